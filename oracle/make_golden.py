@@ -1,0 +1,188 @@
+"""Generate ``tests/golden/`` from the UNMODIFIED reference (build container only).
+
+TEST INFRASTRUCTURE.  Run as ``python -m oracle.make_golden`` from the repo root while
+``/root/reference`` is mounted.  Inputs are small seeded tensors; outputs are whatever
+the reference's own functions / scripts / compiled extension produce on CPU
+(``oracle/ref_harness.py``; SAE with one torch thread, because the reference's
+``index_put_`` on duplicate indices races across CPU threads).  The committed files pin
+the in-repo restatement (``tests/test_oracle_golden.py``) and, through it, the CUDA path.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh  # noqa: E402
+from frlw_evd_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# driver fixtures: (tag, sensor, dataset flag, duration us, rate ev/s, [(mode, name, seed, header)])
+DRIVER_CASES = [
+    ("gen1", "gen1", "gen1", 400000, 1.0e6, [("train", "rec0", 1000, True), ("test", "rec1", 1001, False)]),
+    ("gen4", "gen4", "gen4", 250000, 2.0e6, [("train", "rec0", 1002, True), ("test", "rec1", 1003, False)]),
+]
+DRIVER_SCRIPTS = {
+    "count_image": "generate_eventcountimage.py",
+    "sae": "generate_surfaceofactiveevents.py",
+    "event_volume": "generate_eventvolume.py",
+    "taf": "generate_taf.py",
+}
+
+
+def small_events(seed, H, W, n, t_hi):
+    """Seeded small-grid events with many duplicate pixels and tied timestamps."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = np.sort(rng.integers(0, t_hi, n))
+    x = np.where(rng.random(n) < 0.3, rng.integers(0, 4, n), rng.integers(0, W, n))
+    y = np.where(rng.random(n) < 0.3, rng.integers(0, 3, n), rng.integers(0, H, n))
+    p = rng.integers(0, 2, n)
+    return np.stack([x, y, t, p], axis=1).astype(np.float64)
+
+
+def encoder_golden():
+    out = {}
+    H, W, n = 24, 40, 6000
+    ev = small_events(11, H, W, n, 50000)
+    out["events"] = ev
+    out["shape"] = np.array([H, W])
+
+    f = rh.load_functions("generate_eventcountimage.py")
+    out["eci"] = f["generate_eventframe"](torch.from_numpy(ev.copy()), (H, W))[0].numpy()
+
+    f = rh.load_functions("generate_eventvolume.py")
+    evn = ev.copy()
+    evn[:, 2] = evn[:, 2] / 50000
+    for K in (5, 8):
+        out["ev_k%d" % K] = f["generate_agile_event_volume_cuda"](torch.from_numpy(evn.copy()), (H, W), 50000, K)[0].numpy()
+    out["events_norm"] = evn
+
+    torch.set_num_threads(1)
+    f = rh.load_functions("generate_surfaceofactiveevents.py")
+    lam = [0.00001, 0.0000025, 0.000001]
+    ev_oob = ev.copy()
+    ev_oob[::97, 0] = W + 3          # rows the SAE bounds filter must drop
+    a, mem, _ = f["generate_leaky_cuda"](torch.from_numpy(ev_oob[:4000].copy()), (H, W), lam, None, np.int64(40000))
+    out["sae_events"] = ev_oob
+    out["sae_out0"], out["sae_mem0"] = a.numpy(), mem.numpy().copy()
+    a, mem, _ = f["generate_leaky_cuda"](torch.from_numpy(ev_oob[4000:].copy()), (H, W), lam, mem, np.int64(50000))
+    out["sae_out1"], out["sae_mem1"] = a.numpy(), mem.numpy().copy()
+    torch.set_num_threads(os.cpu_count())
+
+    f = rh.load_functions("generate_taf.py")
+    K = 8
+    state = torch.zeros((H, W, 2, K)) - 6000
+    outs, states = [], []
+    for it in range(6):
+        sel = (ev[:, 2] >= it * 10000) & (ev[:, 2] < (it + 1) * 10000)
+        e5 = np.concatenate([ev[sel], np.full((int(sel.sum()), 1), float(it))], axis=1)
+        if it in (2, 5):
+            e5 = e5[:0]               # empty bins: no ageing
+        e5[:, 2] = (e5[:, 2] - it * 10000) / (10000 + 1e-8)
+        o, state, _ = f["generate_taf_cuda"](torch.from_numpy(e5.copy()), (H, W), state, K)
+        outs.append(o.numpy().copy())
+        states.append(state.numpy().copy())
+    out["taf_out"], out["taf_state"] = np.stack(outs), np.stack(states)
+    out["taf_leaky"] = f["leaky_transform"](torch.from_numpy(outs[-2]).view(K, 2, H, W)).numpy()
+
+    # data/sparse_ops.py (S1-S6)
+    so = rh.load_sparse_ops()
+    B = 2
+    rng = np.random.Generator(np.random.PCG64(12))
+    b = rng.integers(0, B, n)
+    evb = np.concatenate([b[:, None].astype(np.float64), ev], axis=1)      # (b, x, y, t, p)
+    out["sp_events"] = evb
+    v, st = so.generate_agile_event_volume_cuda(torch.from_numpy(evb.copy()), B, (H, W), 0, None, 50000, 5, 10000)
+    out["sp_agile_full"], out["sp_agile_full_state"] = v.numpy(), st.numpy().copy()
+    inc = evb.copy()
+    inc[:, 3] = 50000 + inc[:, 3] / 5     # events of the next 10 ms step
+    v, st2 = so.generate_agile_event_volume_cuda(torch.from_numpy(inc.copy()), B, (H, W), 60000, st.clone(), 50000, 5, 10000)
+    out["sp_inc_events"] = inc
+    out["sp_agile_inc"], out["sp_agile_inc_state"] = v.numpy(), st2.numpy().copy()
+    v, mem = so.generate_event_volume_cuda(torch.from_numpy(evb.copy()), B, (H, W), 50000, None, 50000, 5, 10000)
+    out["sp_ev"], out["sp_ev_mem"] = v.numpy(), mem.numpy().copy()
+    v2, mem2 = so.generate_event_volume_cuda(torch.from_numpy(inc[:500].copy()), B, (H, W), 60000, mem, 50000, 5, 10000)
+    out["sp_ev2"], out["sp_ev2_mem"] = v2.numpy(), mem2.numpy().copy()
+    c = rng.integers(0, 10, n).astype(np.float64)
+    feat = rng.normal(size=n)
+    ev7 = np.stack([evb[:, 0], evb[:, 1], evb[:, 2], evb[:, 3], c, evb[:, 4], feat], axis=1)
+    out["sp_taf_events"] = ev7
+    out["sp_taf"] = so.generate_taf_cuda(torch.from_numpy(ev7.copy()), B, (H, W), 0, None, 50000, 5, 10000)[0].numpy()
+    out["sp_frame"] = so.generate_event_frame_cuda(torch.from_numpy(evb.copy()), B, (H, W), 0)[0].numpy()
+    loc = np.stack([b, ev[:, 1], ev[:, 0]], axis=1).astype(np.int64)
+    feats = rng.normal(size=(n, 3)).astype(np.float32)
+    dense = so.sparseToDense(torch.from_numpy(loc), torch.from_numpy(feats), (B, H, W))
+    out["sp_loc"], out["sp_feat"], out["sp_dense"] = loc, feats, dense.numpy()
+    l2, f2 = so.denseToSparse(dense)
+    out["sp_d2s_loc"], out["sp_d2s_feat"] = l2.numpy(), f2.numpy()
+
+    # compiled reference extension (N1)
+    sys.path.insert(0, os.path.join(HERE, "_ref"))
+    import event_representations as er
+    Q, abin = 5, 10000
+    start = np.array([1000, 5000], dtype=np.int32)
+    z = np.sort(rng.integers(0, 6, n))
+    tq = start[b] + z * abin + rng.integers(0, abin, n)
+    evq = np.stack([b, ev[:, 0], ev[:, 1], tq, ev[:, 3], z], axis=1).astype(np.float32)
+    out["q_events"], out["q_start"] = evq, start
+    out["q_out"] = er.event_queue_tensor(evq, Q, B, H, W, start, abin)
+
+    np.savez_compressed(os.path.join(GOLDEN, "encoders_small.npz"), **out)
+    return out
+
+
+def _digest_tree(root):
+    digests = {}
+    for d, _, files in os.walk(root):
+        for name in files:
+            path = os.path.join(d, name)
+            with open(path, "rb") as fh:
+                digests[os.path.relpath(path, root)] = hashlib.sha256(fh.read()).hexdigest()
+    return dict(sorted(digests.items()))
+
+
+def write_case(raw, case):
+    _tag, sensor, _flag, duration, rate, recs = case
+    for mode, name, seed, header in recs:
+        synth.write_recording(raw, raw, mode, name, sensor, duration, rate, seed, header=header)
+
+
+def driver_golden():
+    result = {}
+    torch.set_num_threads(1)         # determinism of the reference's SAE scatter
+    for case in DRIVER_CASES:
+        tag, _sensor, flag = case[0], case[1], case[2]
+        with tempfile.TemporaryDirectory() as tmp:
+            raw = os.path.join(tmp, "raw")
+            write_case(raw, case)
+            for rep, script in DRIVER_SCRIPTS.items():
+                target = os.path.join(tmp, "out_" + rep)
+                rh.run_script(script, ["-raw_dir", raw, "-label_dir", raw, "-target_dir", target, "-dataset", flag])
+                result["%s/%s" % (tag, rep)] = _digest_tree(target)
+    torch.set_num_threads(os.cpu_count())
+    with open(os.path.join(GOLDEN, "drivers_digest.json"), "w") as fh:
+        json.dump(result, fh, indent=1, sort_keys=True)
+    return result
+
+
+def main():
+    assert rh.available(), "reference not mounted at " + rh.REFERENCE_ROOT
+    os.makedirs(GOLDEN, exist_ok=True)
+    enc = encoder_golden()
+    drv = driver_golden()
+    print("encoders_small.npz:", len(enc), "arrays;", "drivers_digest.json:",
+          sum(len(v) for v in drv.values()), "files")
+
+
+if __name__ == "__main__":
+    main()
