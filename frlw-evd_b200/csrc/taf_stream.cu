@@ -1,0 +1,684 @@
+// Temporal Active Focus over whole streams (generate_taf.py:160-238) in two steps.
+//
+//  (1) bucketing: a counting sort of the time-ordered events by (sensor tile, 10 ms bin)
+//      into packed 4-byte records  [ d:18 | local pixel:13 | p:1 ],  d = t - bin start.
+//      Three small passes: count (shared-memory histograms per 4096-event chunk),
+//      scan (per tile row, then across tiles), scatter.
+//  (2) the persistent tile kernel: one CTA per sensor tile (a contiguous range of <= 2560
+//      pixels, chosen so that there are <= #SM tiles when possible).  The CTA keeps the
+//      tile's FIFO state -- 2K floats per pixel -- in REGISTERS for the whole stream,
+//      streams its own record list through a ring of TMA bulk copies (cp.async.bulk +
+//      mbarrier), accumulates (count, sum d) per cell with shared-memory atomics, applies
+//      the FIFO push / ageing rule bin by bin, and writes the [2K,H,W] tensor (and the
+//      state) once per window with coalesced stores.  Tiles never talk to each other:
+//      the only cross-tile fact, "did any pixel see an event in this bin"
+//      (generate_taf.py:40-41), is a per-bin flag produced by the bucketing pass.
+//
+// HBM-bound byte/float work: no tensor cores.  Sums of d are exact integers, so the
+// result does not depend on the order in which records are accumulated.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace evrep {
+
+constexpr int kTafThreads = 448;        // threads per tile CTA (448 x 5 slots = 2240 px: a 512x640 grid over 147 SMs)
+constexpr int kMaxSlots = 5;            // pixels per thread held in registers
+constexpr int kChunkRecords = 1024;     // records per TMA bulk copy (4 KB)
+constexpr int kStages = 8;              // ring depth (32 KB in flight per SM)
+constexpr int kBatchBins = 32;          // bins whose offsets are staged in smem at once
+constexpr int kMaxTiles = 2048;
+constexpr int kLocalBins = 4;           // bins covered by a bucketing CTA's smem histogram
+constexpr int kBucketThreads = 512;
+constexpr int kBucketPerThread = 8;     // 4096 events per bucketing CTA
+constexpr uint32_t kDMax = (1u << 18) - 1;
+constexpr float kTafInit = -6000.0f;    // generate_taf.py:207-209
+
+// Exact unsigned division by a runtime constant (Granlund-Montgomery).
+struct FastDiv {
+    uint32_t mul, sh1, sh2, d;
+    static FastDiv make(uint32_t d) {
+        FastDiv f;
+        f.d = d;
+        uint32_t l = 0;
+        while ((1ull << l) < d) ++l;
+        f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+        f.sh1 = l < 1 ? l : 1;
+        f.sh2 = l > 0 ? l - 1 : 0;
+        return f;
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const {
+        uint32_t t1 = __umulhi(mul, n);
+        return (t1 + ((n - t1) >> sh1)) >> sh2;
+    }
+};
+
+struct Batch {            // <= kBatchBins consecutive bins of one window
+    int gbin0;            // first global bin
+    int nb;               // bins in this batch
+    int flags;            // bit0: reset state before; bit1: emit window tensor after
+    int win;              // window index (selects the output slot)
+};
+
+struct StreamPlan {       // device pointers into the scratch buffer
+    const int64_t* w_begin;
+    const int64_t* w_end;
+    const int64_t* w_start;
+    const int32_t* w_nbins;
+    const int32_t* w_binbase;
+    const Batch* batches;
+    uint32_t* counts;     // [n_tiles][TB]  histogram, then scatter cursors
+    uint32_t* bin_any;    // [TB]
+    uint32_t* off_rel;    // [n_tiles][TB+1] record offsets relative to the tile's list
+    uint32_t* tile_total; // [n_tiles]
+    uint32_t* tile_base;  // [n_tiles+1] (multiples of 4 records: 16-byte aligned lists)
+    uint32_t* records;    // [n_events + 4 n_tiles]
+    int n_windows, n_batches, TB, n_tiles, P, H, W;
+    FastDiv div_abin, div_P;
+    uint32_t abin;
+};
+
+struct Classified {
+    int tile, gbin;
+    uint32_t rec;
+    bool ok;
+};
+
+__device__ __forceinline__ Classified classify(const SoA& ev, const StreamPlan& pl, int64_t i, int& w) {
+    Classified c;
+    c.ok = false;
+    while (w < pl.n_windows && i >= __ldg(pl.w_end + w)) ++w;       // chunks rarely span windows
+    if (w >= pl.n_windows || i < __ldg(pl.w_begin + w)) return c;  // event lies in a gap
+    Event e = ev.load(i, pl.H, pl.W);
+    if (!e.ok) return c;
+    const int nb = __ldg(pl.w_nbins + w);
+    if (nb <= 0) return c;
+    int64_t dt = (int64_t)ev.time_us(i) - __ldg(pl.w_start + w);
+    uint32_t z = 0, d = 0;
+    if (dt > 0) {
+        uint32_t u = dt > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)dt;
+        z = pl.div_abin.div(u);
+        if (z > (uint32_t)(nb - 1)) z = nb - 1;      // inclusive right edge of the last bin
+        uint32_t rem = u - z * pl.abin;
+        d = rem > kDMax ? kDMax : rem;
+    }
+    uint32_t pix = (uint32_t)e.y * pl.W + e.x;
+    uint32_t tile = pl.div_P.div(pix);
+    c.tile = (int)tile;
+    c.gbin = __ldg(pl.w_binbase + w) + (int)z;
+    c.rec = (d << 14) | ((pix - tile * pl.P) << 1) | (uint32_t)e.p;
+    c.ok = true;
+    return c;
+}
+
+// First window whose event range ends after event index i.
+__device__ __forceinline__ int first_window(const StreamPlan& pl, int64_t i) {
+    int lo = 0, hi = pl.n_windows;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(pl.w_end + mid) > i) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// Chunk prologue shared by the count and scatter passes: window of the first event and
+// the first global bin the chunk can touch.
+__device__ __forceinline__ void chunk_origin(const SoA& ev, const StreamPlan& pl, int64_t c0, int64_t c1,
+                                             int& w0, int& gb0) {
+    w0 = first_window(pl, c0);
+    gb0 = 0;
+    if (w0 < pl.n_windows) {
+        int64_t i = c0 > pl.w_begin[w0] ? c0 : pl.w_begin[w0];
+        gb0 = pl.w_binbase[w0];
+        if (i < c1 && i < pl.w_end[w0]) {
+            int64_t dt = (int64_t)ev.t[i] - pl.w_start[w0];
+            if (dt > 0) {
+                uint32_t z = pl.div_abin.div(dt > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)dt);
+                int nb = pl.w_nbins[w0];
+                if ((int)z > nb - 1) z = nb > 0 ? nb - 1 : 0;
+                gb0 += (int)z;
+            }
+        }
+    }
+}
+
+template <bool kScatter>
+__global__ void __launch_bounds__(kBucketThreads)
+taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last) {
+    extern __shared__ uint32_t hist[];            // [kLocalBins][n_tiles]
+    __shared__ int s_w0, s_gb0;
+    const int nh = kLocalBins * pl.n_tiles;
+    for (int i = threadIdx.x; i < nh; i += kBucketThreads) hist[i] = 0;
+    const int64_t c0 = ev_first + (int64_t)blockIdx.x * (kBucketThreads * kBucketPerThread);
+    const int64_t c1 = min(c0 + kBucketThreads * kBucketPerThread, ev_last);
+    if (threadIdx.x == 0) {
+        int w0, gb0;
+        chunk_origin(ev, pl, c0, c1, w0, gb0);
+        s_w0 = w0; s_gb0 = gb0;
+    }
+    __syncthreads();
+    const int gb0 = s_gb0;
+    int w = s_w0;
+
+    int key[kBucketPerThread];          // >= 0: smem slot, -1: dropped, -2: out of the local bins
+    uint32_t rank[kBucketPerThread], rec[kBucketPerThread];
+    int far_idx[kBucketPerThread];
+#pragma unroll
+    for (int k = 0; k < kBucketPerThread; ++k) {
+        const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
+        key[k] = -1;
+        if (i >= c1) continue;
+        Classified c = classify(ev, pl, i, w);
+        if (!c.ok) continue;
+        rec[k] = c.rec;
+        const int lb = c.gbin - gb0;
+        if (lb >= 0 && lb < kLocalBins) {
+            key[k] = lb * pl.n_tiles + c.tile;
+            rank[k] = atomicAdd(&hist[key[k]], 1u);
+        } else {                          // unsorted input or a very sparse stream
+            key[k] = -2;
+            far_idx[k] = c.tile * pl.TB + c.gbin;
+            if (!kScatter) { atomicAdd(pl.counts + far_idx[k], 1u); pl.bin_any[c.gbin] = 1u; }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nh; i += kBucketThreads) {
+        const uint32_t c = hist[i];
+        if (!c) continue;
+        const int lb = i / pl.n_tiles, tile = i - lb * pl.n_tiles, gbin = gb0 + lb;
+        if (!kScatter) {
+            atomicAdd(pl.counts + (int64_t)tile * pl.TB + gbin, c);
+            pl.bin_any[gbin] = 1u;
+        } else {
+            hist[i] = pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] +
+                      atomicAdd(pl.counts + (int64_t)tile * pl.TB + gbin, c);
+        }
+    }
+    if (!kScatter) return;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kBucketPerThread; ++k) {
+        if (key[k] >= 0) {
+            pl.records[hist[key[k]] + rank[k]] = rec[k];
+        } else if (key[k] == -2) {
+            const int tile = far_idx[k] / pl.TB, gbin = far_idx[k] - tile * pl.TB;
+            pl.records[pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] +
+                       atomicAdd(pl.counts + far_idx[k], 1u)] = rec[k];
+        }
+    }
+}
+
+// Exclusive scan of one tile's per-bin counts -> relative offsets; counts are zeroed so
+// that the scatter pass can reuse them as cursors.
+__global__ void __launch_bounds__(256)
+taf_scan_rows_kernel(StreamPlan pl) {
+    __shared__ uint32_t warp_sum[8];
+    __shared__ uint32_t s_carry;
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* cnt = pl.counts + (int64_t)tile * pl.TB;
+    uint32_t* off = pl.off_rel + (int64_t)tile * (pl.TB + 1);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < pl.TB; base += 256 * 4) {
+        const int i0 = base + threadIdx.x * 4;
+        uint32_t c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = (i0 + k < pl.TB) ? cnt[i0 + k] : 0u;
+        const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        uint32_t before = s_carry;
+        for (int k = 0; k < wid; ++k) before += warp_sum[k];
+        uint32_t run = before + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < pl.TB) { off[i0 + k] = run; cnt[i0 + k] = 0u; }
+            run += c[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { off[pl.TB] = s_carry; pl.tile_total[tile] = s_carry; }
+}
+
+__global__ void __launch_bounds__(1024)
+taf_scan_tiles_kernel(StreamPlan pl) {         // n_tiles <= kMaxTiles = 2 * 1024
+    __shared__ uint32_t warp_sum[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t c[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = threadIdx.x * 2 + k;
+        c[k] = i < pl.n_tiles ? ((pl.tile_total[i] + 3u) & ~3u) : 0u;
+    }
+    const uint32_t mine = c[0] + c[1];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int k = 0; k < wid; ++k) before += warp_sum[k];
+    uint32_t run = before + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = threadIdx.x * 2 + k;
+        if (i < pl.n_tiles) pl.tile_base[i] = run;
+        run += c[k];
+        if (i == pl.n_tiles - 1) pl.tile_base[pl.n_tiles] = run;
+    }
+}
+
+// ---- mbarrier / TMA bulk-copy primitives (PTX) --------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct TileParams {
+    StreamPlan pl;
+    float* state;          // [H,W,2,K]
+    float* out;            // window w at out + w * out_stride
+    int64_t out_stride;
+    int emit_state;        // write the state after every window (always after the last)
+    double span;           // abin + 1e-8
+};
+
+template <int K, int SLOTS>
+__global__ void __maxnreg__(144)      // 448 threads x 144 registers = one SM's register file
+taf_tile_kernel(TileParams tp) {
+    const StreamPlan& pl = tp.pl;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw);                          // [kStages][kChunkRecords]
+    uint2* acc = reinterpret_cast<uint2*>(smem_raw + kStages * kChunkRecords * 4);    // [2][2P] {n, sum d}
+    uint64_t* full = reinterpret_cast<uint64_t*>(acc + 4 * pl.P);
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(full + kStages);                    // [2][kBatchBins+1]
+    uint32_t* s_any = s_off + 2 * (kBatchBins + 1);                                   // [2][kBatchBins]
+    Batch* s_meta = reinterpret_cast<Batch*>(s_any + 2 * kBatchBins);                 // [2]
+
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int64_t HW = (int64_t)pl.H * pl.W;
+    const int64_t pix0 = (int64_t)tile * pl.P;
+    const int npix = (int)min((int64_t)pl.P, HW - pix0);
+    const uint32_t* my_records = pl.records + pl.tile_base[tile];
+    const uint32_t list_len = (pl.tile_total[tile] + 3u) & ~3u;
+    const int n_chunks = (int)((list_len + kChunkRecords - 1) / kChunkRecords);
+    const uint32_t* my_off = pl.off_rel + (int64_t)tile * (pl.TB + 1);
+
+    auto issue = [&](int c) {           // thread 0 only
+        const uint32_t first = (uint32_t)c * kChunkRecords;
+        const uint32_t bytes = min((uint32_t)kChunkRecords, list_len - first) * 4u;
+        uint64_t* bar = full + (c % kStages);
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(ring + (c % kStages) * kChunkRecords, my_records + first, bytes, bar);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 4 * pl.P; i += kTafThreads) acc[i] = make_uint2(0u, 0u);
+    if (tid == 0) s_meta[0] = pl.batches[0];
+    __syncthreads();
+    if (tid == 0)
+        for (int c = 0; c < n_chunks && c < kStages; ++c) issue(c);
+    {
+        const Batch m0 = s_meta[0];
+        if (tid <= m0.nb) s_off[tid] = my_off[m0.gbin0 + tid];
+        if (tid < m0.nb) s_any[tid] = pl.bin_any[m0.gbin0 + tid];
+    }
+
+    // FIFO state of this thread's pixels: v[slot][polarity][k], k = K-1 newest
+    float v[SLOTS][2][K];
+    const bool first_fresh = (pl.batches[0].flags & 1) != 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int lp = s * kTafThreads + tid;
+        if (lp < npix && !first_fresh) {
+            const float4* src = reinterpret_cast<const float4*>(tp.state + (pix0 + lp) * 2 * K);
+#pragma unroll
+            for (int q = 0; q < 2 * K / 4; ++q) {
+                float4 f = src[q];
+                v[s][(q * 4) / K][(q * 4) % K + 0] = f.x; v[s][(q * 4) / K][(q * 4) % K + 1] = f.y;
+                v[s][(q * 4) / K][(q * 4) % K + 2] = f.z; v[s][(q * 4) / K][(q * 4) % K + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int k = 0; k < K; ++k) v[s][p][k] = kTafInit;
+        }
+    }
+    __syncthreads();
+
+    int ready_chunk = -1;      // highest chunk this thread has observed complete
+    int abuf = 0;              // accumulator buffer for the next bin that has records
+    for (int j = 0; j < pl.n_batches; ++j) {
+        const int buf = j & 1;
+        const Batch meta = s_meta[buf];
+        // prefetch the next batch's offsets / flags (latency hidden behind this batch)
+        Batch nmeta = meta;
+        uint32_t pre_off = 0, pre_any = 0;
+        if (j + 1 < pl.n_batches) {
+            nmeta = pl.batches[j + 1];
+            if (tid <= nmeta.nb) pre_off = my_off[nmeta.gbin0 + tid];
+            if (tid < nmeta.nb) pre_any = pl.bin_any[nmeta.gbin0 + tid];
+        }
+        if (meta.flags & 1) {
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) v[s][p][k] = kTafInit;
+        }
+        for (int b = 0; b < meta.nb; ++b) {
+            const uint32_t o0 = s_off[buf * (kBatchBins + 1) + b], o1 = s_off[buf * (kBatchBins + 1) + b + 1];
+            if (!s_any[buf * kBatchBins + b]) continue;          // nobody saw an event: no ageing
+            const bool have = o1 > o0;
+            uint2* my_acc = acc + abuf * 2 * pl.P;
+            if (have) {
+                uint32_t cur = o0;
+                while (cur < o1) {
+                    const int c = (int)(cur / kChunkRecords);
+                    const uint32_t chunk_end = (uint32_t)(c + 1) * kChunkRecords;
+                    const uint32_t seg_end = o1 < chunk_end ? o1 : chunk_end;
+                    if (c > ready_chunk) { mbar_wait(full + (c % kStages), (uint32_t)(c / kStages) & 1u); ready_chunk = c; }
+                    const uint32_t* stage = ring + (c % kStages) * kChunkRecords;
+                    for (uint32_t r = cur + tid; r < seg_end; r += kTafThreads) {
+                        const uint32_t rec = stage[r & (kChunkRecords - 1)];
+                        uint2* cell = my_acc + (rec & 0x3FFFu);      // 2 * local pixel + p
+                        atomicAdd(&cell->x, 1u);
+                        atomicAdd(&cell->y, rec >> 14);
+                    }
+                    if (seg_end == chunk_end) {                  // stage drained: refill it
+                        __syncthreads();
+                        if (tid == 0 && c + kStages < n_chunks) issue(c + kStages);
+                    }
+                    cur = seg_end;
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int lp = s * kTafThreads + tid;
+                if (lp >= npix) continue;
+                uint4 a = make_uint4(0u, 0u, 0u, 0u);
+                if (have) {
+                    a = *reinterpret_cast<uint4*>(my_acc + 2 * lp);           // {n0, S0, n1, S1}
+                    if (a.x | a.z) *reinterpret_cast<uint4*>(my_acc + 2 * lp) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                const uint32_t nn[2] = {a.x, a.z}, ss[2] = {a.y, a.w};
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    if (nn[p]) {
+                        const float mean = (float)((double)ss[p] / ((double)nn[p] * tp.span)) - 1.0f;
+#pragma unroll
+                        for (int k = 0; k + 1 < K; ++k) v[s][p][k] = v[s][p][k + 1] - 1.0f;
+                        v[s][p][K - 1] = mean;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) v[s][p][k] -= 1.0f;
+                    }
+                }
+            }
+            if (have) abuf ^= 1;
+        }
+        if (meta.flags & 2) {
+            float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
+            const bool write_state = tp.emit_state || (j == pl.n_batches - 1);
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int lp = s * kTafThreads + tid;
+                if (lp >= npix) continue;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) __stcs(o + (int64_t)(2 * k + p) * HW + lp, v[s][p][k]);
+                if (write_state) {
+                    float4* dst = reinterpret_cast<float4*>(tp.state + (pix0 + lp) * 2 * K);
+#pragma unroll
+                    for (int q = 0; q < 2 * K / 4; ++q)
+                        dst[q] = make_float4(v[s][(q * 4) / K][(q * 4) % K + 0], v[s][(q * 4) / K][(q * 4) % K + 1],
+                                             v[s][(q * 4) / K][(q * 4) % K + 2], v[s][(q * 4) / K][(q * 4) % K + 3]);
+                }
+            }
+        }
+        if (j + 1 < pl.n_batches) {
+            const int nb = buf ^ 1;
+            if (tid == 0) s_meta[nb] = nmeta;
+            if (tid <= nmeta.nb) s_off[nb * (kBatchBins + 1) + tid] = pre_off;
+            if (tid < nmeta.nb) s_any[nb * kBatchBins + tid] = pre_any;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------
+struct Layout {
+    int P, n_tiles, slots;
+    int64_t o_wbegin, o_wend, o_wstart, o_wnbins, o_wbinbase, o_batches, meta_bytes;
+    int64_t o_counts, o_binany, o_offrel, o_tiletotal, o_tilebase, o_records, total;
+    int n_batches_max;
+};
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n_batches, Layout& L) {
+    const int64_t HW = (int64_t)H * W;
+    const int sms = sm_count();
+    int64_t P = (HW + sms - 1) / sms;
+    P = (P + 31) / 32 * 32;
+    if (P > kTafThreads * kMaxSlots) P = kTafThreads * kMaxSlots;
+    if (P < 32) P = 32;
+    L.P = (int)P;
+    L.n_tiles = (int)((HW + P - 1) / P);
+    L.slots = (int)((P + kTafThreads - 1) / kTafThreads);
+    if (L.n_tiles > kMaxTiles) return EVREP_ERR_RANGE;
+    if (n_events >= (1ll << 31) || TB >= (1ll << 24) || (int64_t)L.n_tiles * (TB + 1) >= (1ll << 31)) return EVREP_ERR_RANGE;
+    L.n_batches_max = n_batches;
+    int64_t o = 0;
+    L.o_wbegin = o;   o += align_up(8ll * n_windows, 16);
+    L.o_wend = o;     o += align_up(8ll * n_windows, 16);
+    L.o_wstart = o;   o += align_up(8ll * n_windows, 16);
+    L.o_wnbins = o;   o += align_up(4ll * n_windows, 16);
+    L.o_wbinbase = o; o += align_up(4ll * (n_windows + 1), 16);
+    L.o_batches = o;  o += align_up(16ll * n_batches, 16);
+    L.meta_bytes = o;
+    o = align_up(o, 256);
+    L.o_counts = o;   o += align_up(4ll * L.n_tiles * TB, 16);
+    L.o_binany = o;   o += align_up(4ll * TB, 16);
+    L.o_offrel = o;   o += align_up(4ll * L.n_tiles * (TB + 1), 16);
+    L.o_tiletotal = o; o += align_up(4ll * L.n_tiles, 16);
+    L.o_tilebase = o; o += align_up(4ll * (L.n_tiles + 1), 16);
+    o = align_up(o, 256);
+    L.o_records = o;  o += align_up(4ll * (n_events + 4ll * L.n_tiles), 256);
+    L.total = o;
+    return EVREP_OK;
+}
+
+static inline int64_t batches_upper_bound(int n_windows, int64_t TB) {
+    return (int64_t)n_windows + TB / kBatchBins + 1;
+}
+
+template <int K>
+static int launch_tiles(const TileParams& tp, int slots, size_t smem, cudaStream_t st) {
+#define EVREP_TILE(S)                                                                                     \
+    case S:                                                                                               \
+        EVREP_CUDA(cudaFuncSetAttribute(taf_tile_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        taf_tile_kernel<K, S><<<tp.pl.n_tiles, kTafThreads, smem, st>>>(tp);                              \
+        break;
+    switch (slots) {
+        EVREP_TILE(1) EVREP_TILE(2) EVREP_TILE(3) EVREP_TILE(4) EVREP_TILE(5)
+        default: return EVREP_ERR_RANGE;
+    }
+#undef EVREP_TILE
+    EVREP_LAUNCH_CHECK();
+    return EVREP_OK;
+}
+
+}  // namespace evrep
+
+using namespace evrep;
+
+extern "C" {
+
+int64_t evrep_taf_stream_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins, int H, int W) {
+    if (n_events < 0 || n_windows < 0 || total_bins < 0 || H <= 0 || W <= 0) return EVREP_ERR_ARG;
+    Layout L;
+    int rc = make_layout(n_events, n_windows, total_bins, H, W, (int)batches_upper_bound(n_windows, total_bins), L);
+    if (rc) return rc;
+    return L.total;
+}
+
+int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+                     const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W, int K,
+                     const uint16_t* xmap, const uint16_t* ymap, float* state_inout, int emit_state_every_window,
+                     float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
+                     void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream) {
+    if (n_events < 0 || n_windows < 0 || H <= 0 || W <= 0 || abin <= 0 || !state_inout || !scratch) return EVREP_ERR_ARG;
+    if (K != 4 && K != 8) return EVREP_ERR_ARG;
+    if ((uint32_t)abin > kDMax) return EVREP_ERR_RANGE;
+    if (n_windows == 0) return EVREP_OK;
+    if (!windows_host || !out || (n_events > 0 && (!t || !x || !y || !p))) return EVREP_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(state_inout) & 15) || (reinterpret_cast<uintptr_t>(scratch) & 255)) return EVREP_ERR_ARG;
+    cudaStream_t st = as_stream(stream);
+
+    // windows -> bins -> batches (host, O(n_windows + bins / 32))
+    int64_t TB = 0;
+    int64_t prev_end = 0;
+    for (int w = 0; w < n_windows; ++w) {
+        const evrep_taf_window& win = windows_host[w];
+        if (win.ev_begin < prev_end || win.ev_end < win.ev_begin || win.ev_end > n_events || win.n_bins < 0) return EVREP_ERR_ARG;
+        if ((int64_t)win.n_bins * abin >= (1ll << 32)) return EVREP_ERR_RANGE;
+        prev_end = win.ev_end;
+        TB += win.n_bins;
+    }
+    std::vector<Batch> batches;
+    batches.reserve((size_t)batches_upper_bound(n_windows, TB));
+    {
+        int gbin = 0;
+        for (int w = 0; w < n_windows; ++w) {
+            const int nb = windows_host[w].n_bins;
+            int done = 0;
+            do {
+                Batch b;
+                b.gbin0 = gbin + done;
+                b.nb = nb - done < kBatchBins ? nb - done : kBatchBins;
+                b.flags = (done == 0 && windows_host[w].fresh ? 1 : 0) | (done + b.nb >= nb ? 2 : 0);
+                b.win = w;
+                batches.push_back(b);
+                done += b.nb;
+            } while (done < nb);
+            gbin += nb;
+        }
+    }
+    Layout L;
+    int rc = make_layout(n_events, n_windows, TB, H, W, (int)batches.size(), L);
+    if (rc) return rc;
+    if (scratch_bytes < L.total) return EVREP_ERR_SCRATCH;
+
+    // pack and upload the metadata
+    std::vector<unsigned char> meta((size_t)L.meta_bytes, 0);
+    int64_t* hb = reinterpret_cast<int64_t*>(meta.data() + L.o_wbegin);
+    int64_t* he = reinterpret_cast<int64_t*>(meta.data() + L.o_wend);
+    int64_t* hs = reinterpret_cast<int64_t*>(meta.data() + L.o_wstart);
+    int32_t* hn = reinterpret_cast<int32_t*>(meta.data() + L.o_wnbins);
+    int32_t* hbb = reinterpret_cast<int32_t*>(meta.data() + L.o_wbinbase);
+    int32_t base = 0;
+    for (int w = 0; w < n_windows; ++w) {
+        hb[w] = windows_host[w].ev_begin; he[w] = windows_host[w].ev_end; hs[w] = windows_host[w].start_time;
+        hn[w] = windows_host[w].n_bins; hbb[w] = base;
+        base += windows_host[w].n_bins;
+    }
+    hbb[n_windows] = base;
+    memcpy(meta.data() + L.o_batches, batches.data(), batches.size() * sizeof(Batch));
+    char* s = reinterpret_cast<char*>(scratch);
+    EVREP_CUDA(cudaMemcpyAsync(s, meta.data(), (size_t)L.meta_bytes, cudaMemcpyHostToDevice, st));
+    // pageable source: the copy has been staged when the call returns, `meta` may die
+
+    StreamPlan pl;
+    pl.w_begin = reinterpret_cast<const int64_t*>(s + L.o_wbegin);
+    pl.w_end = reinterpret_cast<const int64_t*>(s + L.o_wend);
+    pl.w_start = reinterpret_cast<const int64_t*>(s + L.o_wstart);
+    pl.w_nbins = reinterpret_cast<const int32_t*>(s + L.o_wnbins);
+    pl.w_binbase = reinterpret_cast<const int32_t*>(s + L.o_wbinbase);
+    pl.batches = reinterpret_cast<const Batch*>(s + L.o_batches);
+    pl.counts = reinterpret_cast<uint32_t*>(s + L.o_counts);
+    pl.bin_any = reinterpret_cast<uint32_t*>(s + L.o_binany);
+    pl.off_rel = reinterpret_cast<uint32_t*>(s + L.o_offrel);
+    pl.tile_total = reinterpret_cast<uint32_t*>(s + L.o_tiletotal);
+    pl.tile_base = reinterpret_cast<uint32_t*>(s + L.o_tilebase);
+    pl.records = reinterpret_cast<uint32_t*>(s + L.o_records);
+    pl.n_windows = n_windows; pl.n_batches = (int)batches.size(); pl.TB = (int)TB;
+    pl.n_tiles = L.n_tiles; pl.P = L.P; pl.H = H; pl.W = W;
+    pl.div_abin = FastDiv::make((uint32_t)abin);
+    pl.div_P = FastDiv::make((uint32_t)L.P);
+    pl.abin = (uint32_t)abin;
+
+    TileParams tp;
+    tp.pl = pl; tp.state = state_inout; tp.out = out; tp.out_stride = out_stride;
+    tp.emit_state = emit_state_every_window; tp.span = (double)abin + 1e-8;
+
+    if (TB > 0) {
+        EVREP_CUDA(cudaMemsetAsync(s + L.o_counts, 0, (size_t)(L.o_offrel - L.o_counts), st));   // counts + bin_any
+        const int64_t ev_first = windows_host[0].ev_begin, ev_last = windows_host[n_windows - 1].ev_end;
+        const int64_t per_cta = kBucketThreads * kBucketPerThread;
+        const int64_t grid = (ev_last - ev_first + per_cta - 1) / per_cta;
+        const size_t hist_bytes = (size_t)kLocalBins * L.n_tiles * sizeof(uint32_t);
+        SoA ev{t, x, y, p, xmap, ymap};
+        if (grid > 0) {
+            taf_bucket_kernel<false><<<(unsigned)grid, kBucketThreads, hist_bytes, st>>>(ev, pl, ev_first, ev_last);
+            EVREP_LAUNCH_CHECK();
+        }
+        taf_scan_rows_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
+        EVREP_LAUNCH_CHECK();
+        taf_scan_tiles_kernel<<<1, 1024, 0, st>>>(pl);
+        EVREP_LAUNCH_CHECK();
+        if (grid > 0) {
+            taf_bucket_kernel<true><<<(unsigned)grid, kBucketThreads, hist_bytes, st>>>(ev, pl, ev_first, ev_last);
+            EVREP_LAUNCH_CHECK();
+        }
+    } else {
+        EVREP_CUDA(cudaMemsetAsync(s + L.o_tiletotal, 0, (size_t)(L.o_records - L.o_tiletotal), st));
+    }
+
+    const size_t smem = (size_t)kStages * kChunkRecords * 4 + (size_t)4 * L.P * sizeof(uint2) + kStages * 8 +
+                        2 * (kBatchBins + 1) * 4 + 2 * kBatchBins * 4 + 2 * sizeof(Batch) + 64;
+    if (ev_tiles_begin) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_begin), st));
+    rc = K == 8 ? launch_tiles<8>(tp, L.slots, smem, st) : launch_tiles<4>(tp, L.slots, smem, st);
+    if (rc) return rc;
+    if (ev_tiles_end) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_end), st));
+    return EVREP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+"""Temporal Active Focus -- drop-in for the reference's ``generate_taf.py``.
+
+Same names and signatures: ``taf_cuda``, ``generate_taf_cuda``, ``leaky_transform`` and the
+``-raw_dir -label_dir -target_dir -dataset`` command line (``python -m
+frlw_evd_b200.generate_taf ...``).  The functions run the one-bin CUDA kernel on the
+reference's float64 staging layout; the command line plans all windows of a recording on
+the host (``plan_windows``, ``generate_taf.py:160-187`` of the reference) and runs them
+through the bucketing pass + persistent tile kernel (``ops.taf_stream``).
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass
+from typing import List
+
+import torch
+
+from . import ops
+from .recordings import DeviceRecording, Geometry, dump_u8, iter_recordings, parse_args
+
+ABIN = 10000          # generate_taf.py:99  (delta tau = 10 ms)
+VOLUME_BINS = 8       # :100
+MIN_EVENT_COUNT = 50000000   # :92
+
+
+# ------------------------------------------------------------------ reference functions
+def taf_cuda(x, y, t, p, shape, volume_bins, past_volume):
+    """``generate_taf.py:19-58``: ``x, y, p`` integer tensors, ``t`` float32 in [0, 1].
+    Returns ``(f32 [2K,H,W], f32 state [H,W,2,K], seconds)``."""
+    events = torch.stack([x.double(), y.double(), t.double(), p.double()], dim=1)
+    return generate_taf_cuda(events, shape, past_volume, volume_bins)
+
+
+def generate_taf_cuda(events, shape, past_volume=None, volume_bins=5):
+    """``generate_taf.py:60-67``: ``events`` float64 ``[n, >=4]`` (x, y, t_norm, p[, z])."""
+    tick = time.time()
+    out, state = ops.taf_bin_aos64(events, tuple(shape), int(volume_bins), past_volume)
+    torch.cuda.synchronize()
+    return out, state, time.time() - tick
+
+
+def leaky_transform(ecd):
+    """``generate_taf.py:69-76``: ``255 * max(0, 1 - log1p(-v) / 8.7)``."""
+    return ops.leaky_transform(ecd)
+
+
+# ------------------------------------------------------------------------ window plans
+@dataclass
+class TafWindow:
+    label: int
+    fresh: bool
+    start_time: int
+    end_time: int
+    start_count: int
+    end_count: int
+
+    def n_bins(self, abin=ABIN) -> int:
+        return math.ceil((self.end_time - self.start_time) / abin)
+
+    def as_tuple(self, abin=ABIN):
+        return (self.start_count, self.end_count, self.start_time, self.n_bins(abin), int(self.fresh))
+
+
+def plan_windows(loader, labels, abin=ABIN, volume_bins=VOLUME_BINS, min_event_count=MIN_EVENT_COUNT) -> List[TafWindow]:
+    """All windows of one recording (``generate_taf.py:155-187,237-238``).  A window is
+    *fresh* (state reset, own aligned start) when it starts after the previous window's
+    end; otherwise it continues from the previous end and its end is snapped to the
+    10 ms grid (Python ``round``: half to even) and clamped to the last timestamp."""
+    span = abin * volume_bins
+    t_upper, c_upper = -1e16, -1
+    plan = []
+    for label in labels:
+        end_time = int(label)
+        end_count = loader.seek_time(end_time)
+        if end_count is None:
+            continue
+        loader.seek_event(max(end_count - min_event_count, 0))
+        start_time = int(loader.current_time)
+        if end_time - start_time < span:
+            start_time = end_time - span
+        else:
+            start_time = end_time - round((end_time - start_time - span) / abin) * abin - span
+        fresh = start_time > t_upper
+        if fresh:
+            start_count = loader.seek_time(start_time)
+            if start_count is None or start_time < 0:
+                start_count = 0
+        else:
+            start_count, start_time = c_upper, t_upper
+            end_time = round((end_time - start_time) / abin) * abin + start_time
+            end_time = min(end_time, loader.total_time())
+            end_count = loader.seek_time(end_time)
+        plan.append(TafWindow(label, fresh, int(start_time), int(end_time), int(start_count), int(end_count)))
+        t_upper, c_upper = end_time, end_count
+    return plan
+
+
+def encode_recording(rec: DeviceRecording, plan: List[TafWindow], geom: Geometry, abin=ABIN,
+                     volume_bins=VOLUME_BINS, windows_per_launch=32):
+    """Yield ``(label, u8 [K,2,Ht,Wt])`` for every planned window: slot 0 = newest bin,
+    first half -> ``bins{K/2}``, second half -> ``bins{K}`` (``generate_taf.py:226-235``)."""
+    grid = geom.grid
+    state = ops.taf_fresh_state(grid, volume_bins, rec.events.device)
+    for lo in range(0, len(plan), windows_per_launch):
+        chunk = plan[lo:lo + windows_per_launch]
+        volumes = ops.taf_stream(rec.events, [w.as_tuple(abin) for w in chunk], abin, grid, volume_bins,
+                                 state, geom.coord_maps)
+        for w, vol in zip(chunk, volumes):
+            yield w.label, ops.taf_leaky_u8(vol, volume_bins, geom.target, geom.resize_maps)
+
+
+def main():
+    args = parse_args("gen4")
+    geom = Geometry.for_dataset(args.dataset)
+    half = VOLUME_BINS // 2
+    total_time, total_count = 0.0, 0
+    for mode, name, event_file, labels in iter_recordings(args.raw_dir, args.label_dir):
+        rec = DeviceRecording(event_file)
+        plan = plan_windows(rec.loader, labels)
+        torch.cuda.synchronize()
+        tick = time.time()
+        for label, u8 in encode_recording(rec, plan, geom):
+            fname = name + "_" + str(label) + ".npy"
+            dump_u8(u8[:half], args.target_dir, "taf", mode, "bins{0}".format(half), fname)
+            dump_u8(u8[half:], args.target_dir, "taf", mode, "bins{0}".format(VOLUME_BINS), fname)
+        if mode == "test":
+            total_time += time.time() - tick
+            total_count += len(plan)
+    if total_count:
+        print("Average Representation time: ", total_time / total_count)
+
+
+if __name__ == "__main__":
+    main()

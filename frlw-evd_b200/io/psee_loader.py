@@ -1,0 +1,157 @@
+"""``PSEELoader`` with the reference's API (``src/io/psee_loader.py:13-252``) on top of a
+memory map, plus index-level primitives for the GPU drivers.
+
+The reference moves a file cursor and reads small pieces; here the record array is
+memory-mapped once and the cursor is an event index.  Results are identical, including
+two behaviours the window drivers depend on:
+
+* ``seek_time`` bisects with one-record probes while the bracket is wider than
+  ``term_criterion`` events and returns the probe index on an exact hit -- not
+  necessarily the first event with that timestamp -- leaving the cursor one event
+  further (:206-219);
+* ``load_delta_t`` ends at the first event at/after ``current_time + delta_t`` (:117-159).
+"""
+from __future__ import annotations
+
+import bisect
+
+import numpy as np
+
+from . import dat_events_tools as dat
+from . import npy_events_tools as npy_format
+
+
+class PSEELoader(object):
+    def __init__(self, datfile):
+        self._extension = datfile.split(".")[-1]
+        assert self._extension in ["dat", "npy"], "input file path = {}".format(datfile)
+        with open(datfile, "rb") as fh:
+            if self._extension == "dat":
+                self._start, self.ev_type, self._ev_size, self._size = dat.parse_header(fh)
+                self._dtype = dat.EV_TYPE
+                rec_dtype = dat.RECORD_DTYPE
+                self._decode_dtype = [("t", "u4"), ("x", "u2"), ("y", "u2"), ("p", "u1")]
+            else:
+                self._start, self.ev_type, self._ev_size, self._size, _ = npy_format.parse_header(fh)
+                self._dtype = self.ev_type
+                rec_dtype = np.dtype(self.ev_type)
+                self._decode_dtype = list(self.ev_type)
+        assert self._ev_size != 0
+        self.path = datfile
+        self.records = np.memmap(datfile, dtype=rec_dtype, mode="r", offset=self._start)
+        self._t = self.records["t"]
+        self._ev_count = int(self.records.shape[0])
+        self._pos = 0
+        self.done = False
+        self.current_time = 0
+        self.duration_s = self.total_time() * 1e-6
+
+    # -- index-level primitives (used by the GPU drivers) -------------------------------
+    def time_of(self, index: int) -> int:
+        return int(self._t[index])
+
+    def raw_bytes(self, lo: int = 0, hi: int = None) -> np.ndarray:
+        """Payload bytes of events ``[lo, hi)`` (a uint8 view of the memory map)."""
+        hi = self._ev_count if hi is None else hi
+        return self.records[lo:hi].view(np.uint8)
+
+    @property
+    def position(self) -> int:
+        """Event index of the cursor."""
+        return self._pos
+
+    # -- reference API ---------------------------------------------------------------------
+    def reset(self):
+        self._pos, self.done, self.current_time = 0, False, 0
+
+    def event_count(self):
+        return self._ev_count
+
+    def get_size(self):
+        return self._size
+
+    def __repr__(self):
+        kind = dat.EV_STRING if self._extension == "dat" else "numpy array element"
+        return ("PSEELoader:\n-----------\nEvent Type: {}\nEvent Size: {} bytes\nEvent Count: {}\n"
+                "Duration: {} s \n-----------\n").format(kind, self._ev_size, self._ev_count, self.duration_s)
+
+    def _decode(self, lo, hi):
+        rec = self.records[lo:hi]
+        if self._extension == "dat":
+            return dat.unpack(rec, np.empty(hi - lo, dtype=self._decode_dtype))
+        return np.array(rec, dtype=self._decode_dtype)
+
+    def load_n_events(self, ev_count):
+        ev_count = int(ev_count)
+        left = self._ev_count - self._pos
+        lo = self._pos
+        if ev_count >= left:
+            self.done = True
+            ev_count = left
+            if ev_count > 0:
+                self.current_time = int(self._t[lo + ev_count - 1]) + 1
+        else:
+            self.current_time = int(self._t[lo + ev_count])
+        self._pos = lo + ev_count
+        return self._decode(lo, lo + ev_count)
+
+    def load_delta_t(self, delta_t):
+        if delta_t < 1:
+            raise ValueError("load_delta_t(): delta_t must be at least 1 micro-second: {}".format(delta_t))
+        if self.done or self._pos >= self._ev_count:
+            self.done = True
+            return np.empty((0,), dtype=self._decode_dtype)
+        final_time = self.current_time + delta_t
+        lo = self._pos
+        hi = bisect.bisect_left(self._t, final_time, lo, self._ev_count)   # O(log n) probes of the map
+        # timestamp of the last event the reference's 100k-event batching would have read
+        batches = (hi - lo) // 100000 + 1
+        last_seen = int(self._t[min(self._ev_count, lo + batches * 100000) - 1])
+        self.current_time = final_time if last_seen >= final_time else last_seen + 1
+        self._pos = hi
+        self.done = self._pos >= self._ev_count
+        return self._decode(lo, hi)
+
+    def seek_event(self, ev_count):
+        ev_count = int(ev_count)
+        if ev_count <= 0:
+            self._pos, self.current_time = 0, 0
+        elif ev_count >= self._ev_count:
+            self._pos = self._ev_count
+            self.current_time = int(self._t[-1]) + 1
+        else:
+            self._pos = ev_count
+            self.current_time = int(self._t[ev_count])
+        self.done = self._pos >= self._ev_count
+
+    def seek_time(self, final_time, term_criterion=100000):
+        if final_time > self.total_time():
+            self._pos, self.done = self._ev_count, True
+            self.current_time = self.total_time() + 1
+            return
+        if final_time <= 0:
+            self.reset()
+            return
+        low, high = 0, self._ev_count
+        while high - low > term_criterion:
+            middle = (low + high) // 2
+            probe = int(self._t[middle])
+            if probe > final_time:
+                high = middle
+            elif probe < final_time:
+                low = middle + 1
+            else:
+                self._pos = middle + 1
+                self.current_time = final_time
+                self.done = self._pos >= self._ev_count
+                return middle
+        index = bisect.bisect_left(self._t, final_time, low, high)
+        self.seek_event(index)
+        self.current_time = final_time
+        self.done = self._pos >= self._ev_count
+        return index
+
+    def total_time(self):
+        if not self._ev_count:
+            return 0
+        return int(self._t[-1])

@@ -1,0 +1,382 @@
+"""Torch-tensor front end of the C ABI: device buffers, scratch and launches.
+
+PyTorch is used for device memory, streams and (elsewhere) ``torch.distributed`` only;
+all arithmetic happens in ``libevrep.so``.  Every function here requires CUDA tensors and
+raises if the library or a device is missing -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+COORD_LUT_LEN = 16384
+TAF_INIT = -6000.0
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.EvrepError("libevrep encoders need CUDA tensors; got a %s tensor (no CPU fallback)" % t.device)
+
+
+# ------------------------------------------------------------------------ geometry
+@dataclass
+class CoordMaps:
+    """Device LUTs for the gen4 down-scaling policy (``generate_taf.py:103-104,216-218``)."""
+    xmap: torch.Tensor      # u16 [16384]
+    ymap: torch.Tensor
+
+
+def make_coord_maps(sensor_shape, target_shape, device) -> CoordMaps:
+    """``coord * (target / sensor)`` in float64, truncated; coordinates outside the sensor
+    map to 0xFFFF (dropped)."""
+    (H, W), (Ht, Wt) = sensor_shape, target_shape
+    rh, rw = Ht / H, Wt / W
+
+    def lut(n_in, ratio):
+        full = np.full(COORD_LUT_LEN, 0xFFFF, dtype=np.uint16)
+        full[:n_in] = (np.arange(n_in, dtype=np.float64) * ratio).astype(np.int64).astype(np.uint16)
+        return torch.from_numpy(full).to(device)
+
+    return CoordMaps(xmap=lut(W, rw), ymap=lut(H, rh))
+
+
+def nearest_maps(in_shape, out_shape, device):
+    """Legacy ``F.interpolate(mode='nearest')`` source indices (int32 device tensors)."""
+    def one(n_in, n_out):
+        scale = np.float32(n_in) / np.float32(n_out)
+        idx = np.floor(np.arange(n_out, dtype=np.float32) * scale).astype(np.int64)
+        return torch.from_numpy(np.minimum(idx, n_in - 1).astype(np.int32)).to(device)
+    return one(in_shape[0], out_shape[0]), one(in_shape[1], out_shape[1])
+
+
+# ------------------------------------------------------------------------- scratch
+_scratch = {}
+
+
+def scratch(kind: str, nbytes: int, device) -> torch.Tensor:
+    """Zero-initialised scratch, cached per (device, kind, size).  All kernels leave
+    their scratch zeroed on return, so one allocation serves every call."""
+    key = (str(device), kind, int(nbytes))
+    buf = _scratch.get(key)
+    if buf is None:
+        buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+_workspace = {}
+
+
+def workspace(kind: str, nbytes: int, device) -> torch.Tensor:
+    """Grow-only uninitialised scratch (one buffer per device and kind)."""
+    key = (str(device), kind)
+    buf = _workspace.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _workspace[key] = buf = None          # release before growing
+        buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+        _workspace[key] = buf
+    return buf
+
+
+# -------------------------------------------------------------------- event buffers
+@dataclass
+class EventStream:
+    """Structure-of-arrays device buffers of one (slice of a) recording."""
+    t: torch.Tensor     # uint32 [n]  microseconds
+    x: torch.Tensor     # uint16 [n]
+    y: torch.Tensor     # uint16 [n]
+    p: torch.Tensor     # uint8  [n]
+
+    @property
+    def n(self) -> int:
+        return int(self.t.shape[0])
+
+    @property
+    def device(self):
+        return self.t.device
+
+    @classmethod
+    def from_numpy(cls, t, x, y, p, device="cuda") -> "EventStream":
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)
+        return cls(up(t, np.uint32), up(x, np.uint16), up(y, np.uint16), up(p, np.uint8))
+
+    @classmethod
+    def empty(cls, n: int, device="cuda") -> "EventStream":
+        return cls(torch.empty(n, dtype=torch.uint32, device=device), torch.empty(n, dtype=torch.uint16, device=device),
+                   torch.empty(n, dtype=torch.uint16, device=device), torch.empty(n, dtype=torch.uint8, device=device))
+
+    def slice(self, lo: int, hi: int) -> "EventStream":
+        return EventStream(self.t[lo:hi], self.x[lo:hi], self.y[lo:hi], self.p[lo:hi])
+
+    def to_aos64(self) -> torch.Tensor:
+        """The reference's staging matrix: float64 ``[n,4]`` columns (x, y, t, p)."""
+        out = torch.empty((self.n, 4), dtype=torch.float64, device=self.device)
+        _lib.call("evrep_soa_to_aos64", _ptr(self.t), _ptr(self.x), _ptr(self.y), _ptr(self.p),
+                  self.n, _ptr(out), _stream(self.device))
+        return out
+
+
+def decode_dat(records: torch.Tensor, out: Optional[EventStream] = None) -> EventStream:
+    """Decode raw ``.dat`` payload bytes (uint8 CUDA tensor, 8 bytes per event)."""
+    _need_cuda(records)
+    assert records.dtype == torch.uint8 and records.is_contiguous() and records.numel() % 8 == 0
+    n = records.numel() // 8
+    ev = out if out is not None else EventStream.empty(n, records.device)
+    assert ev.n == n
+    _lib.call("evrep_decode_dat", _ptr(records), n, _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p),
+              _stream(records.device))
+    return ev
+
+
+def _maps(maps: Optional[CoordMaps]):
+    return (_ptr(None), _ptr(None)) if maps is None else (_ptr(maps.xmap), _ptr(maps.ymap))
+
+
+# ------------------------------------------------------------------------- encoders
+def count_accumulate(ev: EventStream, shape, maps=None, counts=None) -> torch.Tensor:
+    H, W = shape
+    if counts is None:
+        counts = scratch("count", 8 * H * W, ev.device).view(torch.int32)
+    xm, ym = _maps(maps)
+    _lib.call("evrep_count_accumulate", _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, H, W, xm, ym,
+              _ptr(counts), _stream(ev.device))
+    return counts
+
+
+def count_finalize(counts, shape, reset=True, out=None) -> torch.Tensor:
+    H, W = shape
+    if out is None:
+        out = torch.empty((2, H, W), dtype=torch.float32, device=counts.device)
+    _lib.call("evrep_count_finalize", _ptr(counts), H, W, _ptr(out), int(bool(reset)), _stream(counts.device))
+    return out
+
+
+def count_image(ev: EventStream, shape, maps=None, out=None) -> torch.Tensor:
+    """E1 on a SoA slice: f32 ``[2,H,W]``."""
+    _need_cuda(ev.t)
+    return count_finalize(count_accumulate(ev, shape, maps), shape, True, out)
+
+
+def count_images_nested(ev: EventStream, sizes: Sequence[int], shape, maps=None):
+    """The driver's last-N windows (``generate_eventcountimage.py:156``) for ascending N,
+    accumulating every event once: returns one f32 ``[2,H,W]`` per N."""
+    sizes = list(sizes)
+    assert sizes == sorted(sizes)
+    outs, done = [], 0
+    counts = None
+    for i, n in enumerate(sizes):
+        take = min(n, ev.n)
+        if take > done:
+            counts = count_accumulate(ev.slice(ev.n - take, ev.n - done), shape, maps, counts)
+            done = take
+        if counts is None:
+            counts = scratch("count", 8 * shape[0] * shape[1], ev.device).view(torch.int32)
+        outs.append(count_finalize(counts, shape, reset=(i == len(sizes) - 1)))
+    return outs
+
+
+def count_image_aos64(events: torch.Tensor, shape) -> torch.Tensor:
+    _need_cuda(events)
+    H, W = shape
+    events = events.contiguous()
+    counts = scratch("count", 8 * H * W, events.device).view(torch.int32)
+    _lib.call("evrep_count_accumulate_aos64", _ptr(events), events.shape[0], events.shape[1], H, W,
+              _ptr(counts), _stream(events.device))
+    return count_finalize(counts, shape, True)
+
+
+def _sae_scalars(now):
+    now_f32 = np.float32(float(now))
+    init = np.float32(now_f32 - np.float32(5000000.0))       # generate_surfaceofactiveevents.py:48
+    return float(init), float(now_f32)
+
+
+def sae(ev: EventStream, shape, lambdas, memory, now, maps=None):
+    """A1 on a SoA slice: ``(f32 [2L,H,W], f32 memory [2,H,W])``."""
+    _need_cuda(ev.t, memory)
+    H, W = shape
+    L = len(lambdas)
+    lam = (ctypes.c_float * L)(*[float(np.float32(v)) for v in lambdas])
+    init, now_f32 = _sae_scalars(now)
+    out = torch.empty((2 * L, H, W), dtype=torch.float32, device=ev.device)
+    mem_out = torch.empty((2, H, W), dtype=torch.float32, device=ev.device)
+    keys = scratch("sae", 8 * H * W, ev.device)
+    xm, ym = _maps(maps)
+    _lib.call("evrep_sae", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, H, W, xm, ym, init, now_f32,
+              ctypes.cast(lam, ctypes.c_void_p), L, _ptr(memory), _ptr(mem_out), _ptr(keys), _ptr(out),
+              _stream(ev.device))
+    return out, mem_out
+
+
+def sae_aos64(events, shape, lambdas, memory, now):
+    _need_cuda(events, memory)
+    H, W = shape
+    L = len(lambdas)
+    events = events.contiguous()
+    lam = (ctypes.c_float * L)(*[float(np.float32(v)) for v in lambdas])
+    init, now_f32 = _sae_scalars(now)
+    out = torch.empty((2 * L, H, W), dtype=torch.float32, device=events.device)
+    mem_out = torch.empty((2, H, W), dtype=torch.float32, device=events.device)
+    keys = scratch("sae", 8 * H * W, events.device)
+    _lib.call("evrep_sae_aos64", _ptr(events), events.shape[0], events.shape[1], H, W, init, now_f32,
+              ctypes.cast(lam, ctypes.c_void_p), L, _ptr(memory), _ptr(mem_out), _ptr(keys), _ptr(out),
+              _stream(events.device))
+    return out, mem_out
+
+
+def event_volume(ev: EventStream, t0: int, tw: int, shape, K: int, maps=None, out=None):
+    """V1 on a SoA slice, ``t_norm = (t - t0) / tw``: f32 ``[2K,H,W]``."""
+    _need_cuda(ev.t)
+    H, W = shape
+    if out is None:
+        out = torch.empty((2 * K, H, W), dtype=torch.float32, device=ev.device)
+    xm, ym = _maps(maps)
+    _lib.call("evrep_event_volume", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, int(t0), int(tw),
+              H, W, K, xm, ym, _ptr(out), _stream(ev.device))
+    return out
+
+
+def event_volume_aos64(events, shape, K: int):
+    _need_cuda(events)
+    H, W = shape
+    events = events.contiguous()
+    out = torch.empty((2 * K, H, W), dtype=torch.float32, device=events.device)
+    _lib.call("evrep_event_volume_aos64", _ptr(events), events.shape[0], events.shape[1], H, W, K, _ptr(out),
+              _stream(events.device))
+    return out
+
+
+def taf_fresh_state(shape, K: int, device) -> torch.Tensor:
+    return torch.full((shape[0], shape[1], 2, K), TAF_INIT, dtype=torch.float32, device=device)
+
+
+def _taf_scratch(shape, device):
+    nbytes = _lib.load().evrep_taf_bin_scratch_bytes(shape[0], shape[1])
+    return scratch("taf_bin", nbytes, device)
+
+
+def taf_bin(ev: EventStream, t_min: int, t_span: float, shape, K: int, state, maps=None,
+            want_out=True, in_place=False):
+    """T1 on a SoA slice: ``(f32 [2K,H,W] or None, new state f32 [H,W,2,K])``."""
+    _need_cuda(ev.t, state)
+    H, W = shape
+    state = state.contiguous()
+    new_state = state if in_place else torch.empty_like(state)
+    out = torch.empty((2 * K, H, W), dtype=torch.float32, device=state.device) if want_out else None
+    xm, ym = _maps(maps)
+    _lib.call("evrep_taf_bin", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, int(t_min), float(t_span),
+              H, W, K, xm, ym, _ptr(state), _ptr(new_state), _ptr(out), _ptr(_taf_scratch(shape, state.device)),
+              _stream(state.device))
+    return out, new_state
+
+
+def taf_bin_aos64(events, shape, K: int, state):
+    _need_cuda(events, state)
+    H, W = shape
+    events = events.contiguous()
+    state = state.contiguous()
+    new_state = torch.empty_like(state)
+    out = torch.empty((2 * K, H, W), dtype=torch.float32, device=state.device)
+    _lib.call("evrep_taf_bin_aos64", _ptr(events), events.shape[0], events.shape[1] if events.dim() == 2 else 5,
+              H, W, K, _ptr(state), _ptr(new_state), _ptr(out), _ptr(_taf_scratch(shape, state.device)),
+              _stream(state.device))
+    return out, new_state
+
+
+def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=None,
+               emit_state_every_window=True, out=None, tile_events=None):
+    """T2: run a list of windows ``(ev_begin, ev_end, start_time, n_bins, fresh)`` through
+    the bucketing pass and the persistent tile kernel.  ``state`` (f32 ``[H,W,2,K]``) is
+    updated IN PLACE.  Returns f32 ``[n_windows, 2K, H, W]``.  ``tile_events``: optional pair
+    of ``torch.cuda.Event(enable_timing=True)`` recorded around the tile kernel."""
+    _need_cuda(ev.t, state)
+    H, W = shape
+    nw = len(windows)
+    arr = (_lib.TafWindow * nw)()
+    total_bins = 0
+    for i, w in enumerate(windows):
+        arr[i] = _lib.TafWindow(int(w[0]), int(w[1]), int(w[2]), int(w[3]), int(w[4]))
+        total_bins += int(w[3])
+    if out is None:
+        out = torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=ev.device)
+    assert state.is_contiguous() and out.is_contiguous()
+    need = _lib.load().evrep_taf_stream_scratch_bytes(ev.n, nw, total_bins, H, W)
+    if need < 0:
+        _lib.check(int(need), "evrep_taf_stream_scratch_bytes")
+    buf = workspace("taf_stream", need, ev.device)
+    xm, ym = _maps(maps)
+    _lib.call("evrep_taf_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+              ctypes.cast(arr, ctypes.c_void_p), nw, int(abin), H, W, K, xm, ym, _ptr(state),
+              int(bool(emit_state_every_window)), _ptr(out), 2 * K * H * W, _ptr(buf), buf.numel(),
+              _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
+    return out
+
+
+def _event(pair, i, device):
+    if pair is None:
+        return ctypes.c_void_p(0)
+    e = pair[i]
+    if not e.cuda_event:          # the CUDA event is created lazily, on first record
+        e.record(torch.cuda.current_stream(device))
+    return ctypes.c_void_p(e.cuda_event)
+
+
+# ------------------------------------------------------------------------ epilogues
+def nearest_resize(volume, target_shape, maps=None):
+    _need_cuda(volume)
+    C, H, W = volume.shape
+    Ht, Wt = target_shape
+    ys, xs = maps if maps is not None else nearest_maps((H, W), (Ht, Wt), volume.device)
+    out = torch.empty((C, Ht, Wt), dtype=torch.float32, device=volume.device)
+    _lib.call("evrep_nearest_resize", _ptr(volume.contiguous()), C, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
+              _stream(volume.device))
+    return out
+
+
+def quantize_u8(volume, clamp255=False, out=None):
+    _need_cuda(volume)
+    volume = volume.contiguous()
+    if out is None:
+        out = torch.empty(volume.shape, dtype=torch.uint8, device=volume.device)
+    _lib.call("evrep_quantize_u8", _ptr(volume), volume.numel(), int(bool(clamp255)), _ptr(out), _stream(volume.device))
+    return out
+
+
+def leaky_transform(ecd):
+    _need_cuda(ecd)
+    src = ecd.contiguous()
+    out = torch.empty_like(src)
+    _lib.call("evrep_leaky_transform", _ptr(src), src.numel(), _ptr(out), _stream(src.device))
+    return out
+
+
+def taf_leaky_u8(volume, K: int, target_shape=None, maps=None, out=None):
+    """``generate_taf.py:226-235`` fused: f32 ``[2K,H,W]`` -> u8 ``[K,2,Ht,Wt]``, slot 0 newest."""
+    _need_cuda(volume)
+    C, H, W = volume.shape
+    assert C == 2 * K
+    Ht, Wt = target_shape if target_shape is not None else (H, W)
+    if (Ht, Wt) != (H, W) and maps is None:
+        maps = nearest_maps((H, W), (Ht, Wt), volume.device)
+    ys, xs = maps if maps is not None else (None, None)
+    if out is None:
+        out = torch.empty((K, 2, Ht, Wt), dtype=torch.uint8, device=volume.device)
+    _lib.call("evrep_taf_leaky_u8", _ptr(volume.contiguous()), K, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
+              _stream(volume.device))
+    return out

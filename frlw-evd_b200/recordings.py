@@ -1,0 +1,94 @@
+"""Shared pieces of the four ``generate_*`` command-line drivers: dataset geometry, the
+``train/val/test`` directory walk, GPU residency of a recording and the raw-uint8 writer.
+
+Layout written (reader contract ``data/dataset.py:241-249,294-308`` of the reference):
+headerless C-order ``uint8`` tensors in files named ``<recording>_<label t>.npy``.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .io import PSEELoader, npy_events_tools
+
+
+@dataclass
+class Geometry:
+    """Sensor / target shapes and the resize policy R1 (``generate_taf.py:93-104,216-222``):
+    a target smaller than the sensor (gen4) is encoded directly on the target grid through
+    truncated float64 coordinate scaling; otherwise (gen1) the encoder runs on the sensor
+    grid and the tensor is nearest-resized."""
+    shape: tuple
+    target: tuple
+    device: str = "cuda"
+    coord_maps: Optional[ops.CoordMaps] = None
+    resize_maps: Optional[tuple] = None
+
+    @classmethod
+    def for_dataset(cls, dataset: str, device="cuda") -> "Geometry":
+        if dataset == "gen4":
+            g = cls((720, 1280), (512, 640), device)
+        else:
+            g = cls((240, 304), (256, 320), device)
+        if g.downscale:
+            g.coord_maps = ops.make_coord_maps(g.shape, g.target, device)
+        else:
+            g.resize_maps = ops.nearest_maps(g.shape, g.target, device)
+        return g
+
+    @property
+    def downscale(self) -> bool:
+        return self.target[0] < self.shape[0]
+
+    @property
+    def grid(self) -> tuple:
+        """The grid the encoder kernels run on."""
+        return self.target if self.downscale else self.shape
+
+    def to_target(self, volume: torch.Tensor) -> torch.Tensor:
+        return volume if self.downscale else ops.nearest_resize(volume, self.target, self.resize_maps)
+
+
+def parse_args(default_dataset: str):
+    parser = argparse.ArgumentParser(description="event-representation generator (B200)")
+    parser.add_argument("-raw_dir", type=str)      # "train, val, test" level directory of the event files
+    parser.add_argument("-label_dir", type=str)    # "train, val, test" level directory of the annotations
+    parser.add_argument("-target_dir", type=str)   # output directory
+    parser.add_argument("-dataset", type=str, default=default_dataset)   # gen1 / gen4
+    return parser.parse_args()
+
+
+def iter_recordings(raw_dir, label_dir):
+    """Yield ``(mode, name, event file, label timestamps)`` like the reference's loops
+    (``generate_taf.py:112-151``): unreadable modes are skipped silently."""
+    for mode in ("train", "val", "test"):
+        try:
+            listing = os.listdir(os.path.join(raw_dir, mode))
+        except Exception:
+            continue
+        for name in [f[:-7] for f in listing if f[-3:] == "dat"]:
+            labels = npy_events_tools.read_label_times(os.path.join(label_dir, mode, name + "_bbox.npy"))
+            yield mode, name, os.path.join(raw_dir, mode, name + "_td.dat"), labels
+
+
+class DeviceRecording:
+    """A recording resident on the GPU: raw payload copied once, decoded by the CUDA
+    decoder into SoA buffers; the memory-mapped loader answers the seek queries."""
+
+    def __init__(self, path: str, device="cuda"):
+        self.loader = PSEELoader(path)
+        raw = torch.from_numpy(np.ascontiguousarray(self.loader.raw_bytes()))
+        if torch.device(device).type == "cuda":
+            raw = raw.pin_memory() if raw.numel() else raw
+        self.events = ops.decode_dat(raw.to(device, non_blocking=True))
+
+
+def dump_u8(tensor_u8: torch.Tensor, *path) -> None:
+    os.makedirs(os.path.join(*path[:-1]), exist_ok=True)
+    tensor_u8.cpu().numpy().tofile(os.path.join(*path))

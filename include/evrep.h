@@ -1,0 +1,195 @@
+/*
+ * evrep.h -- C ABI of libevrep.so, the B200 (sm_100a) event-representation encoders.
+ *
+ * This is the drop-in boundary for the preprocessing hot path of HarmoniaLeo/FRLW-EvD.
+ * The reference has no FFI of its own for this path: its encoders are Python functions
+ * built from ATen ops.  Each entry point below therefore cites the reference function
+ * (file:line, relative to the reference tree) whose GPU work it replaces; the Python
+ * modules in frlw-evd_b200/ re-export the reference's names on top of these symbols and
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C symbols, `int` return: 0 = ok, < 0 = error (evrep_strerror()).
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *   - the library never allocates or frees device memory: inputs, state, outputs and
+ *     scratch are caller-owned (sizes from the evrep_*_scratch_bytes() queries).
+ *   - every call is stream-ordered on `stream` (a cudaStream_t) and never synchronises;
+ *     the Python shims synchronise where the reference's functions block.
+ *   - event streams are structure-of-arrays: t u32 microseconds, x u16, y u16, p u8
+ *     (the decoded record of src/io/psee_loader.py:39-44).  `*_aos64` variants read the
+ *     reference's staging layout instead: a float64 [N, ncols] matrix with columns
+ *     (x, y, t, p[, z]) (generate_taf.py:195), coordinates truncated like `.long()`.
+ *   - `xmap` / `ymap` (nullable) are coordinate look-up tables applied to raw sensor
+ *     coordinates before encoding: the gen4 policy `coord * ratio` in float64, truncated
+ *     (generate_taf.py:103-104,216-218).  NULL = identity.  A LUT always holds
+ *     EVREP_COORD_LUT_LEN u16 entries (the 14-bit coordinate range of a .dat record);
+ *     entries >= W (or H) mark coordinates to drop.
+ *   - events whose (mapped) coordinates fall outside H x W, or whose polarity is not 0/1,
+ *     are dropped (the reference only filters in the SAE encoder,
+ *     generate_surfaceofactiveevents.py:72, and device-asserts elsewhere).
+ *   - no CPU fallback exists: without a CUDA device every compute entry point fails
+ *     with EVREP_ERR_CUDA.
+ */
+#ifndef EVREP_H
+#define EVREP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVREP_VERSION 100
+#define EVREP_COORD_LUT_LEN 16384
+
+#define EVREP_OK            0
+#define EVREP_ERR_ARG      -1   /* null pointer / non-positive size / unsupported K */
+#define EVREP_ERR_CUDA     -2   /* a CUDA runtime call or launch failed */
+#define EVREP_ERR_SCRATCH  -3   /* scratch buffer too small */
+#define EVREP_ERR_RANGE    -4   /* a size exceeds what the packed formats can hold */
+
+typedef void* evrep_stream_t;   /* cudaStream_t */
+
+int         evrep_version(void);
+const char* evrep_strerror(int code);
+/* Last CUDA error string seen by the calling thread ("" if none). */
+const char* evrep_last_cuda_error(void);
+/* SM count / compute capability of the current device (any pointer may be NULL). */
+int         evrep_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- D1: .dat decode ----
+ * src/io/dat_events_tools.py:82-100 (stream_td_data) with EV_TYPE :16 -- 8-byte records
+ * (u32 t, i32 w): x = w & 0x3FFF, y = (w & 0x0FFFC000) >> 14, p = (w & 0x10000000) >> 28.
+ * `records` must be 8-byte aligned. */
+int evrep_decode_dat(const void* records, int64_t n,
+                     uint32_t* t, uint16_t* x, uint16_t* y, uint8_t* p, evrep_stream_t stream);
+/* D4 inverse (tests / compatibility): SoA -> the float64 [N,4] (x, y, t, p) staging matrix
+ * of generate_taf.py:195. */
+int evrep_soa_to_aos64(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
+                       int64_t n, double* events, evrep_stream_t stream);
+
+/* ------------------------------------------------------ E1: Event Count Image --------
+ * generate_eventcountimage.py:19-41 (generate_eventframe).  Counts events per (p, y, x)
+ * into `counts` (u32 [2,H,W]) and writes out[p,y,x] = f(count), f = the float32 running
+ * sum of 0.05 clamped to 1, times 255 (bit-exact with the reference's index_add_).
+ * `counts` must be zero before the first accumulate of a window.  evrep_count_image()
+ * = accumulate + finalize(reset=1).  Nested last-N windows (driver :156) call
+ * accumulate on the extra events and finalize(reset=0) per N. */
+int evrep_count_accumulate(const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n,
+                           int H, int W, const uint16_t* xmap, const uint16_t* ymap,
+                           uint32_t* counts, evrep_stream_t stream);
+int evrep_count_accumulate_aos64(const double* events, int64_t n, int ncols, int H, int W,
+                                 uint32_t* counts, evrep_stream_t stream);
+int evrep_count_finalize(uint32_t* counts, int H, int W, float* out, int reset, evrep_stream_t stream);
+int evrep_count_image(const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n,
+                      int H, int W, const uint16_t* xmap, const uint16_t* ymap,
+                      uint32_t* counts, float* out, evrep_stream_t stream);
+
+/* ------------------------------------------------- A1: Surface of Active Events ------
+ * generate_surfaceofactiveevents.py:71-80 (generate_leaky_cuda) + :44-69 (taf_cuda).
+ * latest[p,y,x] = max float32(t) over the events (the sequential last-writer result for
+ * time-sorted input), `init` where no event; merged by max with `memory_in` when not
+ * NULL; written to `memory_out` (absolute float32 timestamps, may alias memory_in);
+ * out[l,p,y,x] = expf(lambdas[l] * (latest - now_f32)) * 255, out is [2L,H,W].
+ * `init` = f32(f32(now) - 5e6) and `now_f32` = f32(now) are computed by the caller.
+ * `keys` is a u32 [2,H,W] scratch, zero on entry, zero on return.  L <= 8. */
+int evrep_sae(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n,
+              int H, int W, const uint16_t* xmap, const uint16_t* ymap,
+              float init, float now_f32, const float* lambdas_host, int L,
+              const float* memory_in, float* memory_out, uint32_t* keys, float* out,
+              evrep_stream_t stream);
+int evrep_sae_aos64(const double* events, int64_t n, int ncols, int H, int W,
+                    float init, float now_f32, const float* lambdas_host, int L,
+                    const float* memory_in, float* memory_out, uint32_t* keys, float* out,
+                    evrep_stream_t stream);
+
+/* ------------------------------------------------------------ V1: Event Volume -------
+ * generate_eventvolume.py:15-42 (generate_agile_event_volume_cuda).  Temporal bilinear
+ * splat: t* = K * f32(t_norm), centres 1..K, weight 1 - |c - t*| into channel
+ * 2(c-1) + (1-p); out [2K,H,W] = sum / 5 * 255.  SoA form: t_norm = (t - t0) / tw in
+ * float64 (driver :141).  `out` doubles as the accumulator (it is zeroed by the call). */
+int evrep_event_volume(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
+                       int64_t n, int64_t t0, int64_t tw, int H, int W, int K,
+                       const uint16_t* xmap, const uint16_t* ymap, float* out, evrep_stream_t stream);
+int evrep_event_volume_aos64(const double* events, int64_t n, int ncols, int H, int W, int K,
+                             float* out, evrep_stream_t stream);
+
+/* ------------------------------------------- T1: Temporal Active Focus, one bin ------
+ * generate_taf.py:60-67 (generate_taf_cuda) + :19-58 (taf_cuda).  One 10 ms step of the
+ * per-(y,x,p) K-deep FIFO: active cells shift and push mean(f32(t_norm) - 1), inactive
+ * cells age by 1; a bin without any (valid) event leaves the state untouched.
+ * state layout f32 [H,W,2,K]; out (nullable) f32 [2K,H,W], channel 2k + p.
+ * SoA form: t_norm = (t - t_min) / t_span in float64 (driver :213-215, t_span = abin+1e-8).
+ * `scratch`: evrep_taf_bin_scratch_bytes(H, W) bytes, zero on entry, zero on return.
+ * state_out may alias state_in.  K in {1..16}. */
+int64_t evrep_taf_bin_scratch_bytes(int H, int W);
+int evrep_taf_bin(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
+                  int64_t n, int64_t t_min, double t_span, int H, int W, int K,
+                  const uint16_t* xmap, const uint16_t* ymap,
+                  const float* state_in, float* state_out, float* out, void* scratch,
+                  evrep_stream_t stream);
+int evrep_taf_bin_aos64(const double* events, int64_t n, int ncols, int H, int W, int K,
+                        const float* state_in, float* state_out, float* out, void* scratch,
+                        evrep_stream_t stream);
+
+/* ------------------------------------- T2: Temporal Active Focus, whole streams ------
+ * The driver loop of generate_taf.py:160-238 for a list of windows, in two launches
+ * groups: (1) events are bucketed by (sensor tile, 10 ms bin) into packed 4-byte records,
+ * (2) one persistent kernel walks all windows: each CTA owns a tile of the sensor, keeps
+ * that tile's FIFO state in registers, consumes its records bin by bin (TMA bulk copies
+ * into shared memory), and emits the [2K,H,W] tensor (+ the state) at every window end.
+ *
+ * A window w covers events [ev_begin, ev_end) (indices into the SoA arrays) and bins
+ * i = 0..n_bins-1 of width `abin` starting at start_time; an event belongs to bin
+ * clamp(floor((t - start_time) / abin), 0, n_bins - 1) -- the reference's inclusive
+ * edges with the later bin winning (:201-202).  `fresh` resets the state to -6000
+ * (:205-209) before the window.  Windows must be ordered and non-overlapping.
+ * Per-cell mean: exact integer sum of (t - t_min) over the bin, divided in float64 by
+ * n * (abin + 1e-8), minus 1 -- order independent, hence deterministic; equals the
+ * reference's sequential float32 sum to rounding (bit-exact for n == 1).
+ *
+ * out: f32 [n_windows][2K,H,W] (window w at out + w * out_stride floats).
+ * state_inout: f32 [H,W,2,K]; read unless windows[0].fresh, written after the last window
+ * (and after every window when emit_state_every_window != 0).
+ * K must be 4 or 8; abin <= 262143; at most 2048 tiles of 2560 pixels.
+ * ev_tiles_begin / ev_tiles_end: optional cudaEvent_t handles recorded on `stream` right
+ * before / after the tile kernel (the dominant launch), for live roofline timing. */
+typedef struct {
+    int64_t ev_begin;
+    int64_t ev_end;
+    int64_t start_time;
+    int32_t n_bins;
+    int32_t fresh;
+} evrep_taf_window;
+
+int64_t evrep_taf_stream_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins, int H, int W);
+int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
+                     int64_t n_events, const evrep_taf_window* windows_host, int n_windows,
+                     int abin, int H, int W, int K,
+                     const uint16_t* xmap, const uint16_t* ymap,
+                     float* state_inout, int emit_state_every_window,
+                     float* out, int64_t out_stride,
+                     void* scratch, int64_t scratch_bytes,
+                     void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream);
+
+/* ------------------------------------------------- T3 / R1 / W1: output epilogues ----
+ * evrep_nearest_resize: F.interpolate(mode='nearest') as used at generate_taf.py:222 --
+ * out[c, Y, X] = in[c, ysrc[Y], xsrc[X]] with the legacy index maps (int32, device).
+ * evrep_quantize_u8: the `.astype(np.uint8)` of the drivers (float -> uint8 truncation),
+ * with the Event Volume clamp `np.where(v > 255, 255, v)` (generate_eventvolume.py:155-157)
+ * when clamp255 != 0.
+ * evrep_taf_leaky_u8: generate_taf.py:226-235 fused -- leaky_transform (:69-76),
+ * view [K,2,Ht,Wt], flip of the slot axis, nearest resize, uint8 truncation.  `out` is
+ * u8 [K,2,Ht,Wt] with slot 0 = newest: its first half is the bins{K/2} file and its
+ * second half the bins{K} file (data/dataset.py:294-308). */
+int evrep_nearest_resize(const float* in, int C, int H, int W, int Ht, int Wt,
+                         const int32_t* ysrc, const int32_t* xsrc, float* out, evrep_stream_t stream);
+int evrep_quantize_u8(const float* in, int64_t n, int clamp255, uint8_t* out, evrep_stream_t stream);
+int evrep_taf_leaky_u8(const float* volume, int K, int H, int W, int Ht, int Wt,
+                       const int32_t* ysrc, const int32_t* xsrc, uint8_t* out, evrep_stream_t stream);
+int evrep_leaky_transform(const float* in, int64_t n, float* out, evrep_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVREP_H */

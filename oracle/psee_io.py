@@ -10,6 +10,8 @@ non-leftmost index on an exact probe hit and then leaves the cursor one event la
 """
 from __future__ import annotations
 
+import bisect
+
 import numpy as np
 
 RECORD = np.dtype([("t", "<u4"), ("w", "<i4")])                       # dat_events_tools.py:16
@@ -129,7 +131,7 @@ class Loader:
                 self.current_time = final_time
                 self.done = self._cursor >= self._ev_count
                 return middle
-        idx = low + int(np.searchsorted(self._rec["t"][low:high], final_time))
+        idx = bisect.bisect_left(self._rec["t"], final_time, low, high)
         self.seek_event(idx)
         self.current_time = final_time
         self.done = self._cursor >= self._ev_count
@@ -160,7 +162,7 @@ class Loader:
             return np.empty((0,), dtype=DECODED)
         final_time = self.current_time + delta_t
         start = self._cursor
-        stop = start + int(np.searchsorted(self._rec["t"][start:], final_time))
+        stop = bisect.bisect_left(self._rec["t"], final_time, start, self._ev_count)
         # the reference reads 100k-event batches until one ends at/after final_time (or
         # EOF) and cuts the LAST batch with searchsorted; for time-sorted files the result
         # is the slice [start, first index with t >= final_time).

@@ -1,0 +1,168 @@
+"""Parity of the CUDA encoders (through the C ABI) with the CPU oracle and the golden
+vectors recorded from the reference.  Integer results bit-exact; float results within
+the north-star tolerance 1e-5 relative / 1e-6 absolute."""
+import numpy as np
+import pytest
+import torch
+
+from frlw_evd_b200 import ops, synth
+from oracle import encoders as oe
+from oracle import psee_io
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+LAMBDAS = [0.00001, 0.0000025, 0.000001]
+DEV = "cuda"
+
+
+def close(a, b):
+    a = a.cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return np.allclose(a, b, rtol=RTOL, atol=ATOL)
+
+
+def exact(a, b):
+    a = a.cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return np.array_equal(a, b)
+
+
+def stream(H, W, dur, rate, seed):
+    t, x, y, p = synth.make_stream(H, W, dur, rate, seed)
+    aos = torch.from_numpy(np.stack([x, y, t, p], 1).astype(np.float64))
+    return (t, x, y, p), aos
+
+
+def test_decode_dat_bit_exact():
+    (t, x, y, p), _ = stream(720, 1280, 20000, 5e6, 5)
+    rec = synth.pack_dat_records(t, x, y, p)
+    for n in (len(t), len(t) - 3, 1, 0):
+        raw = torch.from_numpy(rec[:n].view(np.uint8).copy()).to(DEV)
+        ev = ops.decode_dat(raw)
+        want = psee_io.decode_records(rec[:n].view(psee_io.RECORD))
+        assert exact(ev.t, want["t"]) and exact(ev.x, want["x"]) and exact(ev.y, want["y"]) and exact(ev.p, want["p"])
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    assert exact(ev.to_aos64(), np.stack([x, y, t, p], 1).astype(np.float64))
+
+
+def test_count_image_golden_and_stream(golden):
+    H, W = [int(v) for v in golden["shape"]]
+    got = ops.count_image_aos64(torch.from_numpy(golden["events"]).to(DEV), (H, W))
+    assert exact(got, golden["eci"])
+    (t, x, y, p), aos = stream(240, 304, 50000, 4e6, 1000)
+    want = oe.count_image(aos, (240, 304))
+    assert exact(ops.count_image_aos64(aos.to(DEV), (240, 304)), want)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    assert exact(ops.count_image(ev, (240, 304)), want)
+    # nested last-N windows == independent encodes of events[-N:]
+    outs = ops.count_images_nested(ev, [50000, 100000, 300000], (240, 304))
+    for n, o in zip([50000, 100000, 300000], outs):
+        assert exact(o, oe.count_image(aos[-n:], (240, 304)))
+    # scratch is left clean
+    assert exact(ops.count_image(ev.slice(0, 0), (240, 304)), np.zeros((2, 240, 304), np.float32))
+
+
+def test_count_image_gen4_policy():
+    (t, x, y, p), aos = stream(720, 1280, 40000, 10e6, 1002)
+    scaled = aos.clone()
+    scaled[:, 0] *= 640 / 1280
+    scaled[:, 1] *= 512 / 720
+    want = oe.count_image(scaled, (512, 640))
+    maps = ops.make_coord_maps((720, 1280), (512, 640), DEV)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    assert exact(ops.count_image(ev, (512, 640), maps), want)
+    assert exact(ops.count_image_aos64(scaled.to(DEV), (512, 640)), want)
+
+
+def test_sae_golden(golden):
+    H, W = [int(v) for v in golden["shape"]]
+    ev = torch.from_numpy(golden["sae_events"]).to(DEV)
+    o0, m0 = ops.sae_aos64(ev[:4000], (H, W), LAMBDAS, None, np.int64(40000))
+    assert exact(m0, golden["sae_mem0"]) and close(o0, golden["sae_out0"])
+    o1, m1 = ops.sae_aos64(ev[4000:], (H, W), LAMBDAS, m0, np.int64(50000))
+    assert exact(m1, golden["sae_mem1"]) and close(o1, golden["sae_out1"])
+
+
+def test_sae_stream_state_bit_exact():
+    (t, x, y, p), aos = stream(240, 304, 6_000_000, 2e5, 1001)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    cut = len(t) // 2
+    now0, now1 = int(t[cut - 1]) + 1, int(t[-1]) + 1
+    w0, wm0 = oe.sae_surfaces(aos[:cut], (240, 304), LAMBDAS, None, np.int64(now0))
+    w1, wm1 = oe.sae_surfaces(aos[cut:], (240, 304), LAMBDAS, wm0, np.int64(now1))
+    g0, gm0 = ops.sae(ev.slice(0, cut), (240, 304), LAMBDAS, None, now0)
+    g1, gm1 = ops.sae(ev.slice(cut, len(t)), (240, 304), LAMBDAS, gm0, now1)
+    assert exact(gm0, wm0) and exact(gm1, wm1)          # float32-rounded timestamps: bit-exact
+    assert close(g0, w0) and close(g1, w1)
+
+
+@pytest.mark.parametrize("K", [5, 8])
+def test_event_volume_golden(golden, K):
+    H, W = [int(v) for v in golden["shape"]]
+    got = ops.event_volume_aos64(torch.from_numpy(golden["events_norm"]).to(DEV), (H, W), K)
+    assert close(got, golden["ev_k%d" % K])
+
+
+def test_event_volume_config1_gen1_k8():
+    """BASELINE config 1: Event Volume K=8, GEN1, one 50 ms window (~200k events)."""
+    (t, x, y, p), aos = stream(240, 304, 50000, 4e6, 1000)
+    norm = aos.clone()
+    norm[:, 2] = (norm[:, 2] - 0) / 50000
+    want = oe.event_volume(norm, (240, 304), 8)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    assert close(ops.event_volume(ev, 0, 50000, (240, 304), 8), want)
+    assert close(ops.event_volume_aos64(norm.to(DEV), (240, 304), 8), want)
+
+
+def test_taf_bin_golden_sequence(golden):
+    H, W = [int(v) for v in golden["shape"]]
+    ev = golden["events"]
+    K = 8
+    state = ops.taf_fresh_state((H, W), K, DEV)
+    for it in range(6):
+        sel = (ev[:, 2] >= it * 10000) & (ev[:, 2] < (it + 1) * 10000)
+        e5 = np.concatenate([ev[sel], np.full((int(sel.sum()), 1), float(it))], axis=1)
+        if it in (2, 5):
+            e5 = e5[:0]
+        e5[:, 2] = (e5[:, 2] - it * 10000) / (10000 + 1e-8)
+        out, state = ops.taf_bin_aos64(torch.from_numpy(e5).to(DEV), (H, W), K, state)
+        assert close(out, golden["taf_out"][it]), it
+        assert close(state, golden["taf_state"][it]), it
+    assert close(ops.leaky_transform(torch.from_numpy(golden["taf_out"][4]).to(DEV)), golden["taf_leaky"].reshape(16, H, W))
+
+
+def test_taf_bin_soa_gen4_policy():
+    (t, x, y, p), aos = stream(720, 1280, 30000, 10e6, 1002)
+    maps = ops.make_coord_maps((720, 1280), (512, 640), DEV)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    K = 8
+    want_state = oe.taf_fresh_state((512, 640), K)
+    got_state = ops.taf_fresh_state((512, 640), K, DEV)
+    for it in range(3):
+        lo, hi = np.searchsorted(t, [it * 10000, (it + 1) * 10000])
+        e5 = torch.cat([aos[lo:hi], torch.zeros(hi - lo, 1, dtype=torch.float64)], 1).clone()
+        e5[:, 2] = (e5[:, 2] - it * 10000) / (10000 + 1e-8)
+        e5[:, 0] *= 0.5
+        e5[:, 1] *= 512 / 720
+        want_out, want_state = oe.taf_bin_update(e5, (512, 640), want_state, K)
+        got_out, got_state = ops.taf_bin(ev.slice(lo, hi), it * 10000, 10000 + 1e-8, (512, 640), K, got_state, maps)
+        assert close(got_out, want_out) and close(got_state, want_state)
+
+
+def test_epilogues():
+    g = torch.Generator().manual_seed(0)
+    vol = torch.rand((16, 240, 304), generator=g) * 300 - 20
+    vol_d = vol.to(DEV)
+    want = torch.nn.functional.interpolate(vol[None], size=(256, 320), mode="nearest")[0]
+    assert exact(ops.nearest_resize(vol_d, (256, 320)), want)
+    pos = vol.clamp(min=0)
+    assert exact(ops.quantize_u8(pos.to(DEV), clamp255=True), np.where(pos.numpy() > 255, 255, pos.numpy()).astype(np.uint8))
+    state = -torch.rand((16, 240, 304), generator=g) * 7
+    state[::3] = -6000.0
+    ref = oe.leaky_transform(oe.nearest_resize(state, (256, 320)).view(8, 2, 256, 320)).numpy()
+    ref = np.flip(ref, axis=0).astype(np.uint8)
+    got = ops.taf_leaky_u8(state.to(DEV), 8, (256, 320)).cpu().numpy()
+    # uint8 truncation of a float: allow the 1-LSB flips of log1pf vs the CPU kernel
+    diff = np.abs(got.astype(int) - ref.astype(int))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3

@@ -1,0 +1,99 @@
+"""The whole-stream TAF path (bucketing + persistent tile kernel) against the oracle's
+bin-by-bin execution of the same windows.  Float tolerance 1e-5 rel / 1e-6 abs."""
+import numpy as np
+import pytest
+import torch
+
+from frlw_evd_b200 import generate_taf as gt
+from frlw_evd_b200 import ops, synth
+from oracle import encoders as oe
+
+from helpers import oracle_taf_windows
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+DEV = "cuda"
+
+
+def close(a, b):
+    return np.allclose(a.cpu().numpy(), b.cpu().numpy() if torch.is_tensor(b) else b, rtol=RTOL, atol=ATOL)
+
+
+def idx(t, v):
+    return int(np.searchsorted(t, v))
+
+
+@pytest.mark.parametrize("K", [8, 4])
+def test_small_grid_mixed_windows(K):
+    """Fresh + incremental windows, a long first window (> 32 bins), empty bins, a gap in
+    the event range, a zero-bin window and an event exactly on a bin edge."""
+    H, W, abin = 24, 40, 1000
+    rng = np.random.Generator(np.random.PCG64(5))
+    n = 30000
+    t = np.sort(rng.integers(0, 120000, n)).astype(np.uint32)
+    t[(t >= 50000) & (t < 53000)] = 49999            # three empty bins
+    t[100] = 1000                                     # exactly on an edge: later bin wins
+    t = np.sort(t)
+    x = np.where(rng.random(n) < 0.4, rng.integers(0, 3, n), rng.integers(0, W, n)).astype(np.uint16)
+    y = np.where(rng.random(n) < 0.4, rng.integers(0, 2, n), rng.integers(0, H, n)).astype(np.uint16)
+    p = rng.integers(0, 2, n).astype(np.uint8)
+    windows = [
+        (0, idx(t, 60000), 0, 60, 1),                               # 60 bins: two batches
+        (idx(t, 60000), idx(t, 65000), 60000, 5, 0),
+        (idx(t, 65000), idx(t, 65000), 65000, 0, 0),                # zero bins: state re-emitted
+        (idx(t, 65000), idx(t, 72500), 65000, 8, 0),                # last bin half filled
+        (idx(t, 90000), idx(t, 98000), 90000, 8, 1),                # gap, then fresh
+        (idx(t, 98000), idx(t, 104000), 98000, 6, 0),
+    ]
+    want, want_state = oracle_taf_windows(t, x, y, p, windows, abin, (H, W), K)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    state = ops.taf_fresh_state((H, W), K, DEV)
+    got = ops.taf_stream(ev, windows, abin, (H, W), K, state)
+    for i in range(len(windows)):
+        assert close(got[i], want[i]), i
+    assert close(state, want_state)
+    # determinism: integer sums make the result independent of record order
+    state2 = ops.taf_fresh_state((H, W), K, DEV)
+    again = ops.taf_stream(ev, windows, abin, (H, W), K, state2)
+    assert torch.equal(got, again) and torch.equal(state, state2)
+    # continuing from a saved state == one launch over all windows
+    s3 = ops.taf_fresh_state((H, W), K, DEV)
+    a = ops.taf_stream(ev, windows[:2], abin, (H, W), K, s3)
+    b = ops.taf_stream(ev, windows[2:4], abin, (H, W), K, s3)
+    assert torch.equal(torch.cat([a, b]), got[:4])
+
+
+def test_gen1_recording_plan_and_tensors(tmp_path):
+    (t, x, y, p), labels = synth.write_recording(str(tmp_path), str(tmp_path), "train", "r", "gen1", 400000, 1e6, 1000)
+    from frlw_evd_b200.recordings import DeviceRecording
+    rec = DeviceRecording(str(tmp_path / "train" / "r_td.dat"))
+    plan = gt.plan_windows(rec.loader, labels)
+    windows = [w.as_tuple() for w in plan]
+    want, _ = oracle_taf_windows(t, x, y, p, windows, 10000, (240, 304), 8)
+    state = ops.taf_fresh_state((240, 304), 8, DEV)
+    got = ops.taf_stream(rec.events, windows, 10000, (240, 304), 8, state)
+    for i in range(len(windows)):
+        assert close(got[i], want[i]), i
+
+
+def test_gen4_policy_recording(tmp_path):
+    (t, x, y, p), labels = synth.write_recording(str(tmp_path), str(tmp_path), "train", "r", "gen4", 200000, 5e6, 1002)
+    from frlw_evd_b200.recordings import DeviceRecording, Geometry
+    rec = DeviceRecording(str(tmp_path / "train" / "r_td.dat"))
+    geom = Geometry.for_dataset("gen4")
+    plan = gt.plan_windows(rec.loader, labels)
+    windows = [w.as_tuple() for w in plan]
+    want, want_state = oracle_taf_windows(t, x, y, p, windows, 10000, (512, 640), 8, scale=(640 / 1280, 512 / 720))
+    state = ops.taf_fresh_state((512, 640), 8, DEV)
+    got = ops.taf_stream(rec.events, windows, 10000, (512, 640), 8, state, geom.coord_maps)
+    for i in range(len(windows)):
+        assert close(got[i], want[i]), i
+    assert close(state, want_state)
+    # stream path == bin-by-bin CUDA path (property that also holds at full benchmark size)
+    s2 = ops.taf_fresh_state((512, 640), 8, DEV)
+    w0 = windows[0]
+    for b in range(w0[3]):
+        lo, hi = idx(t, w0[2] + b * 10000), idx(t, w0[2] + (b + 1) * 10000)
+        out, s2 = ops.taf_bin(rec.events.slice(max(lo, w0[0]), min(hi, w0[1])), w0[2] + b * 10000, 10000 + 1e-8,
+                              (512, 640), 8, s2, geom.coord_maps)
+    assert close(out, got[0])

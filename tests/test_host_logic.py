@@ -1,0 +1,102 @@
+"""Host-side logic on CPU: the PSEELoader mirror and the TAF window planner against the
+oracle restatement (itself pinned to the reference), file formats, label parsing."""
+import numpy as np
+import pytest
+
+from frlw_evd_b200 import generate_taf as gt
+from frlw_evd_b200 import synth
+from frlw_evd_b200.io import PSEELoader, dat_events_tools, npy_events_tools
+from oracle import drivers as od
+from oracle import psee_io
+
+
+@pytest.fixture(scope="module")
+def recording(tmp_path_factory):
+    root = tmp_path_factory.mktemp("rec")
+    (t, x, y, p), labels = synth.write_recording(str(root), str(root), "train", "a", "gen1", 600000, 1e6, 7)
+    synth.write_recording(str(root), str(root), "val", "b", "gen1", 300000, 5e5, 8, header=False)
+    return root, (t, x, y, p), labels
+
+
+def test_header_and_decode(recording):
+    root, (t, x, y, p), _ = recording
+    with open(root / "train" / "a_td.dat", "rb") as fh:
+        start, ev_type, ev_size, size = dat_events_tools.parse_header(fh)
+    assert (ev_type, ev_size, size) == (0, 8, [240, 304]) and start > 0
+    with open(root / "val" / "b_td.dat", "rb") as fh:
+        assert dat_events_tools.parse_header(fh) == (0, 0, 8, [None, None])     # headerless
+    ev = dat_events_tools.load_td_data(str(root / "train" / "a_td.dat"), 1000, 10)
+    assert np.array_equal(ev["t"], t[10:1010]) and np.array_equal(ev["x"], x[10:1010])
+    assert np.array_equal(ev["y"], y[10:1010]) and np.array_equal(ev["p"], p[10:1010])
+    assert dat_events_tools.count_events(str(root / "train" / "a_td.dat")) == len(t)
+
+
+def test_write_event_buffer_round_trip(tmp_path):
+    t, x, y, p = synth.make_stream(240, 304, 10000, 1e6, 3)
+    buf = np.empty(len(t), dtype=[("t", "u4"), ("x", "u2"), ("y", "u2"), ("p", "u1")])
+    buf["t"], buf["x"], buf["y"], buf["p"] = t, x, y, p
+    fh = dat_events_tools.write_header(str(tmp_path / "w_td.dat"), 240, 304)
+    dat_events_tools.write_event_buffer(fh, buf)
+    fh.close()
+    back = PSEELoader(str(tmp_path / "w_td.dat")).load_n_events(len(t))
+    for k in "txyp":
+        assert np.array_equal(back[k], buf[k])
+
+
+def test_loader_matches_oracle_on_random_operations(recording):
+    root, (t, _, _, _), _ = recording
+    path = str(root / "train" / "a_td.dat")
+    a, b = psee_io.Loader(path), PSEELoader(path)
+    rng = np.random.default_rng(0)
+    mid = len(t) // 2
+    for _ in range(1500):
+        op = int(rng.integers(0, 4))
+        if op == 0:
+            q = int(rng.choice([rng.integers(-5, 700000), t[rng.integers(0, len(t))], t[mid], t[mid // 2]]))
+            assert a.seek_time(q) == b.seek_time(q)
+        elif op == 1:
+            q = int(rng.integers(-3, len(t) + 3))
+            a.seek_event(q), b.seek_event(q)
+        elif op == 2:
+            if a._cursor >= len(t):
+                continue
+            q = int(rng.integers(0, 250000))
+            ra, rb = a.load_n_events(q), b.load_n_events(q)
+            assert all(np.array_equal(ra[k], rb[k]) for k in "txyp")
+        else:
+            q = int(rng.integers(1, 300000))
+            ra, rb = a.load_delta_t(q), b.load_delta_t(q)
+            assert all(np.array_equal(ra[k], rb[k]) for k in "txyp")
+        assert (a.current_time, a.done, a._cursor) == (b.current_time, b.done, b.position)
+    with pytest.raises(ValueError):
+        b.load_delta_t(0)
+
+
+def test_label_times_new_and_legacy_names(tmp_path):
+    times = np.arange(100000, 400000, 50000)
+    synth.write_bbox_npy(str(tmp_path / "n_bbox.npy"), times)
+    synth.write_bbox_npy(str(tmp_path / "l_bbox.npy"), times, legacy_names=True)
+    for name in ("n_bbox.npy", "l_bbox.npy"):
+        got = npy_events_tools.read_label_times(str(tmp_path / name))
+        assert np.array_equal(got, times) and np.array_equal(got, psee_io.read_label_times(str(tmp_path / name)))
+
+
+@pytest.mark.parametrize("labels", [
+    np.arange(100000, 600000, 50000),
+    np.array([90000, 95000, 97000, 250000, 251000, 420000, 599999, 700000]),   # snapping, zero bins, gaps, past EOF
+])
+def test_taf_window_plan_matches_oracle(recording, labels):
+    root, _, _ = recording
+    path = str(root / "train" / "a_td.dat")
+    plan = gt.plan_windows(PSEELoader(path), labels, min_event_count=200000)
+    loader = psee_io.Loader(path)
+    t_upper, c_upper, want = -1e16, -1, []
+    for label in labels:
+        w = od.taf_window_plan(loader, label, t_upper, c_upper, 10000, 80000, 200000)
+        if w is None:
+            continue
+        want.append(w)
+        t_upper, c_upper = w[2], w[4]
+    got = [(w.fresh, w.start_time, w.end_time, w.start_count, w.end_count) for w in plan]
+    assert got == [tuple(w) for w in want] and len(got) >= 5
+    assert any(not w.fresh for w in plan) and sum(w.fresh for w in plan) >= 1
