@@ -4,7 +4,7 @@
 //      into packed 4-byte records  [ d:18 | local pixel:13 | p:1 ],  d = t - bin start.
 //      Three small passes: count (shared-memory histograms per 4096-event chunk),
 //      scan (per tile row, then across tiles), scatter.
-//  (2) the persistent tile kernel: one CTA per sensor tile (a contiguous range of <= 2560
+//  (2) the persistent tile kernel: one CTA per sensor tile (a contiguous range of <= 2304
 //      pixels, chosen so that there are <= #SM tiles when possible).  The CTA keeps the
 //      tile's FIFO state -- 2K floats per pixel -- in REGISTERS for the whole stream,
 //      streams its own record list through a ring of TMA bulk copies (cp.async.bulk +
@@ -24,8 +24,8 @@
 
 namespace evrep {
 
-constexpr int kTafThreads = 448;        // threads per tile CTA (448 x 5 slots = 2240 px: a 512x640 grid over 147 SMs)
-constexpr int kMaxSlots = 5;            // pixels per thread held in registers
+constexpr int kTafThreads = 384;        // threads per tile CTA: 3 warps per SM sub-partition -> up to 168 registers
+constexpr int kMaxSlots = 6;            // pixels per thread held in registers (6 x 384 = 2304 >= 2240)
 constexpr int kChunkRecords = 1024;     // records per TMA bulk copy (4 KB)
 constexpr int kStages = 8;              // ring depth (32 KB in flight per SM)
 constexpr int kBatchBins = 32;          // bins whose offsets are staged in smem at once
@@ -314,7 +314,7 @@ struct TileParams {
 };
 
 template <int K, int SLOTS>
-__global__ void __maxnreg__(144)      // 448 threads x 144 registers = one SM's register file
+__global__ void __launch_bounds__(kTafThreads, 1)
 taf_tile_kernel(TileParams tp) {
     const StreamPlan& pl = tp.pl;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -538,7 +538,7 @@ static int launch_tiles(const TileParams& tp, int slots, size_t smem, cudaStream
         taf_tile_kernel<K, S><<<tp.pl.n_tiles, kTafThreads, smem, st>>>(tp);                              \
         break;
     switch (slots) {
-        EVREP_TILE(1) EVREP_TILE(2) EVREP_TILE(3) EVREP_TILE(4) EVREP_TILE(5)
+        EVREP_TILE(1) EVREP_TILE(2) EVREP_TILE(3) EVREP_TILE(4) EVREP_TILE(5) EVREP_TILE(6)
         default: return EVREP_ERR_RANGE;
     }
 #undef EVREP_TILE

@@ -46,6 +46,21 @@ class PSEELoader(object):
         self.current_time = 0
         self.duration_s = self.total_time() * 1e-6
 
+    @classmethod
+    def from_records(cls, records: np.ndarray) -> "PSEELoader":
+        """A loader over an in-memory ``.dat`` record array (no file behind it)."""
+        self = cls.__new__(cls)
+        self._extension, self._start, self.ev_type, self._ev_size, self._size = "dat", 0, 0, 8, [None, None]
+        self._dtype = dat.EV_TYPE
+        self._decode_dtype = [("t", "u4"), ("x", "u2"), ("y", "u2"), ("p", "u1")]
+        self.path = None
+        self.records = records.view(dat.RECORD_DTYPE) if records.dtype != dat.RECORD_DTYPE else records
+        self._t = self.records["t"]
+        self._ev_count = int(self.records.shape[0])
+        self._pos, self.done, self.current_time = 0, False, 0
+        self.duration_s = self.total_time() * 1e-6
+        return self
+
     # -- index-level primitives (used by the GPU drivers) -------------------------------
     def time_of(self, index: int) -> int:
         return int(self._t[index])

@@ -151,7 +151,7 @@ int evrep_taf_bin_aos64(const double* events, int64_t n, int ncols, int H, int W
  * out: f32 [n_windows][2K,H,W] (window w at out + w * out_stride floats).
  * state_inout: f32 [H,W,2,K]; read unless windows[0].fresh, written after the last window
  * (and after every window when emit_state_every_window != 0).
- * K must be 4 or 8; abin <= 262143; at most 2048 tiles of 2560 pixels.
+ * K must be 4 or 8; abin <= 262143; at most 2048 tiles of 2304 pixels.
  * ev_tiles_begin / ev_tiles_end: optional cudaEvent_t handles recorded on `stream` right
  * before / after the tile kernel (the dominant launch), for live roofline timing. */
 typedef struct {

@@ -189,6 +189,38 @@ def taf_window_plan(loader, label, t_upper, c_upper, abin=10000, span=80000, min
     return False, start_time, end_time, start_count, end_count
 
 
+def taf_windows_in_memory(staged, windows, abin, grid, K, scale=None, state=None):
+    """The inner loops of ``generate_taf.py:195-222`` on an in-memory staging matrix
+    (float64 ``[N,4]`` x, y, t, p) for a list of ``(ev_begin, ev_end, start_time, n_bins,
+    fresh)`` windows.  Returns ``(list of [2K,H,W] tensors, final state)``.  Used by the
+    parity tests and as the timed CPU baseline of ``bench.py``."""
+    outs = []
+    if state is None:
+        state = enc.taf_fresh_state(grid, K)
+    for (lo, hi, start, n_bins, fresh) in windows:
+        ev = staged[lo:hi]
+        z = torch.zeros_like(ev[:, 0])
+        for i in range(n_bins):
+            a, b = start + i * abin, start + (i + 1) * abin
+            z = torch.where((ev[:, 2] >= a) & (ev[:, 2] <= b), torch.zeros_like(z) + i, z)
+        ev = torch.cat([ev, z[:, None]], dim=1)
+        if fresh:
+            state = enc.taf_fresh_state(grid, K)
+        vol = None
+        for i in range(n_bins):
+            e = ev[ev[:, 4] == i]
+            t_min, t_max = start + i * abin, start + (i + 1) * abin
+            e[:, 2] = (e[:, 2] - t_min) / (t_max - t_min + 1e-8)
+            if scale is not None:
+                e[:, 0] *= scale[0]
+                e[:, 1] *= scale[1]
+            vol, state = enc.taf_bin_update(e, grid, state, K)
+        if vol is None:
+            vol = state.permute(3, 2, 0, 1).contiguous().view(2 * K, grid[0], grid[1])
+        outs.append(vol)
+    return outs, state
+
+
 def run_taf(raw_dir, label_dir, target_dir, dataset="gen4"):
     """``generate_taf.py:78-243``."""
     shape, target = _geometry(dataset)
