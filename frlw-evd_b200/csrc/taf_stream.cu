@@ -304,13 +304,39 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct TileParams {
     StreamPlan pl;
     float* state;          // [H,W,2,K]
     float* out;            // window w at out + w * out_stride
     int64_t out_stride;
     int emit_state;        // write the state after every window (always after the last)
-    double span;           // abin + 1e-8
+    int bulk_out;          // out rows are 16-byte aligned: emit through smem + TMA bulk stores
+    float span;            // f32(abin + 1e-8)
+};
+
+// Shared-memory carve-up of the tile kernel (all offsets multiples of 128 bytes).
+struct TileSmem {
+    int ring, acc, stage, bars, off, any, meta, total;
+    __host__ __device__ TileSmem(int P, int K) {
+        int o = 0;
+        ring = o;  o += kStages * kChunkRecords * 4;
+        acc = o;   o += 2 * P * (int)sizeof(uint2);                 // {n, sum d} per (pixel, polarity)
+        stage = o; o += 2 * K * P * 4;                              // [2K][P] output staging
+        bars = o;  o += 128;
+        off = o;   o += 2 * (kBatchBins + 1) * 4; o = (o + 127) / 128 * 128;
+        any = o;   o += 2 * kBatchBins * 4;
+        meta = o;  o += 2 * (int)sizeof(Batch); o = (o + 127) / 128 * 128;
+        total = o;
+    }
 };
 
 template <int K, int SLOTS>
@@ -318,12 +344,14 @@ __global__ void __launch_bounds__(kTafThreads, 1)
 taf_tile_kernel(TileParams tp) {
     const StreamPlan& pl = tp.pl;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw);                          // [kStages][kChunkRecords]
-    uint2* acc = reinterpret_cast<uint2*>(smem_raw + kStages * kChunkRecords * 4);    // [2][2P] {n, sum d}
-    uint64_t* full = reinterpret_cast<uint64_t*>(acc + 4 * pl.P);
-    uint32_t* s_off = reinterpret_cast<uint32_t*>(full + kStages);                    // [2][kBatchBins+1]
-    uint32_t* s_any = s_off + 2 * (kBatchBins + 1);                                   // [2][kBatchBins]
-    Batch* s_meta = reinterpret_cast<Batch*>(s_any + 2 * kBatchBins);                 // [2]
+    const TileSmem lay(pl.P, K);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + lay.ring);     // [kStages][kChunkRecords]
+    uint2* acc = reinterpret_cast<uint2*>(smem_raw + lay.acc);             // [2P]
+    float* stage = reinterpret_cast<float*>(smem_raw + lay.stage);         // [2K][P]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(smem_raw + lay.off);     // [2][kBatchBins+1]
+    uint32_t* s_any = reinterpret_cast<uint32_t*>(smem_raw + lay.any);     // [2][kBatchBins]
+    Batch* s_meta = reinterpret_cast<Batch*>(smem_raw + lay.meta);         // [2]
 
     const int tid = threadIdx.x, tile = blockIdx.x;
     const int64_t HW = (int64_t)pl.H * pl.W;
@@ -346,7 +374,7 @@ taf_tile_kernel(TileParams tp) {
         for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 4 * pl.P; i += kTafThreads) acc[i] = make_uint2(0u, 0u);
+    for (int i = tid; i < 2 * pl.P; i += kTafThreads) acc[i] = make_uint2(0u, 0u);
     if (tid == 0) s_meta[0] = pl.batches[0];
     __syncthreads();
     if (tid == 0)
@@ -381,7 +409,8 @@ taf_tile_kernel(TileParams tp) {
     __syncthreads();
 
     int ready_chunk = -1;      // highest chunk this thread has observed complete
-    int abuf = 0;              // accumulator buffer for the next bin that has records
+    int next_refill = kStages; // next chunk to load; its stage is free once chunk (next_refill - kStages) is drained
+    bool staged_once = false;
     for (int j = 0; j < pl.n_batches; ++j) {
         const int buf = j & 1;
         const Batch meta = s_meta[buf];
@@ -405,28 +434,35 @@ taf_tile_kernel(TileParams tp) {
             const uint32_t o0 = s_off[buf * (kBatchBins + 1) + b], o1 = s_off[buf * (kBatchBins + 1) + b + 1];
             if (!s_any[buf * kBatchBins + b]) continue;          // nobody saw an event: no ageing
             const bool have = o1 > o0;
-            uint2* my_acc = acc + abuf * 2 * pl.P;
             if (have) {
                 uint32_t cur = o0;
                 while (cur < o1) {
                     const int c = (int)(cur / kChunkRecords);
                     const uint32_t chunk_end = (uint32_t)(c + 1) * kChunkRecords;
                     const uint32_t seg_end = o1 < chunk_end ? o1 : chunk_end;
+                    if (c >= next_refill) {
+                        // a single bin longer than the whole ring: recycle drained stages now
+                        __syncthreads();
+                        if (tid == 0)
+                            for (int r = next_refill; r <= c && r < n_chunks; ++r) issue(r);
+                        next_refill = c + 1;
+                    }
                     if (c > ready_chunk) { mbar_wait(full + (c % kStages), (uint32_t)(c / kStages) & 1u); ready_chunk = c; }
-                    const uint32_t* stage = ring + (c % kStages) * kChunkRecords;
+                    const uint32_t* chunk = ring + (c % kStages) * kChunkRecords;
                     for (uint32_t r = cur + tid; r < seg_end; r += kTafThreads) {
-                        const uint32_t rec = stage[r & (kChunkRecords - 1)];
-                        uint2* cell = my_acc + (rec & 0x3FFFu);      // 2 * local pixel + p
+                        const uint32_t rec = chunk[r & (kChunkRecords - 1)];
+                        uint2* cell = acc + (rec & 0x3FFFu);         // 2 * local pixel + p
                         atomicAdd(&cell->x, 1u);
                         atomicAdd(&cell->y, rec >> 14);
                     }
-                    if (seg_end == chunk_end) {                  // stage drained: refill it
-                        __syncthreads();
-                        if (tid == 0 && c + kStages < n_chunks) issue(c + kStages);
-                    }
                     cur = seg_end;
                 }
-                __syncthreads();
+                __syncthreads();                                  // all records of the bin are in `acc`
+                // every chunk that ends at or before o1 is drained: refill those ring stages
+                const int drained = (int)(o1 / kChunkRecords);    // chunks [0, drained) fully consumed
+                if (tid == 0)
+                    for (int r = next_refill; r < drained + kStages && r < n_chunks; ++r) issue(r);
+                if (drained + kStages > next_refill) next_refill = drained + kStages;
             }
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
@@ -434,37 +470,67 @@ taf_tile_kernel(TileParams tp) {
                 if (lp >= npix) continue;
                 uint4 a = make_uint4(0u, 0u, 0u, 0u);
                 if (have) {
-                    a = *reinterpret_cast<uint4*>(my_acc + 2 * lp);           // {n0, S0, n1, S1}
-                    if (a.x | a.z) *reinterpret_cast<uint4*>(my_acc + 2 * lp) = make_uint4(0u, 0u, 0u, 0u);
+                    a = *reinterpret_cast<uint4*>(acc + 2 * lp);              // {n0, S0, n1, S1}
+                    if (a.x | a.z) *reinterpret_cast<uint4*>(acc + 2 * lp) = make_uint4(0u, 0u, 0u, 0u);
                 }
                 const uint32_t nn[2] = {a.x, a.z}, ss[2] = {a.y, a.w};
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
-                    if (nn[p]) {
-                        const float mean = (float)((double)ss[p] / ((double)nn[p] * tp.span)) - 1.0f;
+                    // mean(t_norm) - 1 = S / (n * span) - 1 (generate_taf.py:23-27), branch free
+                    const bool active = nn[p] != 0u;
+                    const float denom = (float)(active ? nn[p] : 1u) * tp.span;
+                    const float mean = __fdividef((float)ss[p], denom) - 1.0f;
+                    float aged[K];
 #pragma unroll
-                        for (int k = 0; k + 1 < K; ++k) v[s][p][k] = v[s][p][k + 1] - 1.0f;
-                        v[s][p][K - 1] = mean;
-                    } else {
+                    for (int k = 0; k < K; ++k) aged[k] = v[s][p][k] - 1.0f;
 #pragma unroll
-                        for (int k = 0; k < K; ++k) v[s][p][k] -= 1.0f;
-                    }
+                    for (int k = 0; k + 1 < K; ++k) v[s][p][k] = active ? aged[k + 1] : aged[k];
+                    v[s][p][K - 1] = active ? mean : aged[K - 1];
                 }
             }
-            if (have) abuf ^= 1;
+            if (have) __syncthreads();                             // `acc` is clean again for the next bin
         }
         if (meta.flags & 2) {
-            float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
             const bool write_state = tp.emit_state || (j == pl.n_batches - 1);
+            float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
+            if (tp.bulk_out) {
+                // [2K][npix] staging tile -> one TMA bulk store per channel row
+                if (staged_once) {
+                    if (tid < 2 * K) bulk_wait_read();             // previous window's rows have left smem
+                    __syncthreads();
+                }
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                const int lp = s * kTafThreads + tid;
-                if (lp >= npix) continue;
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int lp = s * kTafThreads + tid;
+                    if (lp >= npix) continue;
 #pragma unroll
-                for (int k = 0; k < K; ++k)
+                    for (int k = 0; k < K; ++k)
 #pragma unroll
-                    for (int p = 0; p < 2; ++p) __stcs(o + (int64_t)(2 * k + p) * HW + lp, v[s][p][k]);
-                if (write_state) {
+                        for (int p = 0; p < 2; ++p) stage[(2 * k + p) * pl.P + lp] = v[s][p][k];
+                }
+                fence_async_smem();
+                __syncthreads();
+                if (tid < 2 * K) {
+                    bulk_store_1d(o + (int64_t)tid * HW, stage + tid * pl.P, (uint32_t)npix * 4u);
+                    bulk_commit();
+                }
+                staged_once = true;
+            } else {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int lp = s * kTafThreads + tid;
+                    if (lp >= npix) continue;
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) __stcs(o + (int64_t)(2 * k + p) * HW + lp, v[s][p][k]);
+                }
+            }
+            if (write_state) {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int lp = s * kTafThreads + tid;
+                    if (lp >= npix) continue;
                     float4* dst = reinterpret_cast<float4*>(tp.state + (pix0 + lp) * 2 * K);
 #pragma unroll
                     for (int q = 0; q < 2 * K / 4; ++q)
@@ -481,6 +547,7 @@ taf_tile_kernel(TileParams tp) {
         }
         __syncthreads();
     }
+    if (tp.bulk_out && tid < 2 * K) bulk_wait_all();               // smem must outlive the bulk reads
 }
 
 // ---- host side -------------------------------------------------------------------------
@@ -647,7 +714,9 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
 
     TileParams tp;
     tp.pl = pl; tp.state = state_inout; tp.out = out; tp.out_stride = out_stride;
-    tp.emit_state = emit_state_every_window; tp.span = (double)abin + 1e-8;
+    tp.emit_state = emit_state_every_window;
+    tp.span = (float)((double)abin + 1e-8);
+    tp.bulk_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
 
     if (TB > 0) {
         EVREP_CUDA(cudaMemsetAsync(s + L.o_counts, 0, (size_t)(L.o_offrel - L.o_counts), st));   // counts + bin_any
@@ -672,8 +741,7 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
         EVREP_CUDA(cudaMemsetAsync(s + L.o_tiletotal, 0, (size_t)(L.o_records - L.o_tiletotal), st));
     }
 
-    const size_t smem = (size_t)kStages * kChunkRecords * 4 + (size_t)4 * L.P * sizeof(uint2) + kStages * 8 +
-                        2 * (kBatchBins + 1) * 4 + 2 * kBatchBins * 4 + 2 * sizeof(Batch) + 64;
+    const size_t smem = (size_t)TileSmem(L.P, K).total;
     if (ev_tiles_begin) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_begin), st));
     rc = K == 8 ? launch_tiles<8>(tp, L.slots, smem, st) : launch_tiles<4>(tp, L.slots, smem, st);
     if (rc) return rc;
