@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=10.0, help="recording length (default: the 100 M-event workload)")
     ap.add_argument("--rate", type=float, default=1e7)
-    ap.add_argument("--cpu-windows", type=int, default=12, help="windows in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-windows", type=int, default=120, help="windows in the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -188,7 +188,7 @@ def main():
     out = torch.empty((nw, 2 * K, GRID[0], GRID[1]), dtype=torch.float32, device=dev)
 
     def step(events=None):
-        ops.taf_stream(ev, windows, ABIN, GRID, K, state, maps, True, out, events)
+        ops.taf_stream(ev, windows, ABIN, GRID, K, state, maps, False, out, events)
 
     def barrier():
         if world > 1:
@@ -222,14 +222,20 @@ def main():
         total_events = float(n_in_windows)
     value = total_events / (ms * 1e-3) / 1e6
 
-    # roofline of the dominant kernel (the tile kernel): SURVEY.md §8d algorithmic bytes
+    # roofline of the dominant kernel (the tile kernel).  Algorithmic bytes: events read
+    # (9 B each) + one f32 [2K,H,W] tensor written per window + the state written once.
+    # SURVEY.md §8d also counts a state write per window; the kernel keeps the state in
+    # registers between windows, so those bytes are not moved and are NOT counted here.
     peak, peak_src = load_peaks()
-    algo_bytes = 9 * n_in_windows + nw * 2 * (4 * 2 * K * HW)
+    algo_bytes = 9 * n_in_windows + nw * (4 * 2 * K * HW) + 4 * 2 * K * HW
+    survey_bytes = 9 * n_in_windows + nw * 2 * (4 * 2 * K * HW)
     achieved = algo_bytes / (tile_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "taf_tile_kernel<8,5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "taf_tile_kernel<8,6>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": tile_ms,
-                "step_frac": algo_bytes / (ms * 1e-3) / 1e9 / peak}
+                "step_frac": algo_bytes / (ms * 1e-3) / 1e9 / peak,
+                "note": "state kept on chip between windows: per-window state writes of SURVEY 8d are not moved and not counted",
+                "frac_if_survey_formula_were_used": survey_bytes / (tile_ms * 1e-3) / 1e9 / peak}
     traffic_file = os.path.join(ROOT, "profiles", "taf_tile_traffic.json")
     if os.path.isfile(traffic_file):
         with open(traffic_file) as fh:
@@ -248,7 +254,7 @@ def main():
         def e2e_step():
             raw_dev.copy_(raw_host, non_blocking=True)
             ops.decode_dat(raw_dev, dec)
-            ops.taf_stream(dec, windows, ABIN, GRID, K, st2, maps, True, out)
+            ops.taf_stream(dec, windows, ABIN, GRID, K, st2, maps, False, out)
             for w in range(nw):
                 ops.taf_leaky_u8(out[w], K, out=u8_dev[w])
             u8_host.copy_(u8_dev, non_blocking=True)

@@ -42,7 +42,7 @@ SIGNATURES = {
     "evrep_taf_bin": (c_int, [P, P, P, P, c_int64, c_int64, c_double, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "evrep_taf_bin_aos64": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "evrep_taf_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int64, c_int, c_int]),
-    "evrep_taf_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int,
+    "evrep_taf_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int,
                                  P, c_int64, P, c_int64, P, P, P]),
     "evrep_nearest_resize": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "evrep_quantize_u8": (c_int, [P, c_int64, c_int, P, P]),

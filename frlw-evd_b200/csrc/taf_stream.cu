@@ -29,7 +29,7 @@ constexpr int kMaxSlots = 6;            // pixels per thread held in registers (
 constexpr int kChunkRecords = 1024;     // records per TMA bulk copy (4 KB)
 constexpr int kStages = 8;              // ring depth (32 KB in flight per SM)
 constexpr int kBatchBins = 32;          // bins whose offsets are staged in smem at once
-constexpr int kMaxTiles = 2048;
+constexpr int kMaxTiles = 2048;         // kLocalBins * kMaxTiles counters fit the 13-bit key of the scatter pass
 constexpr int kLocalBins = 4;           // bins covered by a bucketing CTA's smem histogram
 constexpr int kBucketThreads = 512;
 constexpr int kBucketPerThread = 8;     // 4096 events per bucketing CTA
@@ -80,37 +80,17 @@ struct StreamPlan {       // device pointers into the scratch buffer
     uint32_t abin;
 };
 
-struct Classified {
-    int tile, gbin;
-    uint32_t rec;
-    bool ok;
+// Window descriptor staged in shared memory by the bucketing kernels.
+struct WinInfo {
+    int64_t begin, end, start;
+    int nbins, binbase;
 };
 
-__device__ __forceinline__ Classified classify(const SoA& ev, const StreamPlan& pl, int64_t i, int& w) {
-    Classified c;
-    c.ok = false;
-    while (w < pl.n_windows && i >= __ldg(pl.w_end + w)) ++w;       // chunks rarely span windows
-    if (w >= pl.n_windows || i < __ldg(pl.w_begin + w)) return c;  // event lies in a gap
-    Event e = ev.load(i, pl.H, pl.W);
-    if (!e.ok) return c;
-    const int nb = __ldg(pl.w_nbins + w);
-    if (nb <= 0) return c;
-    int64_t dt = (int64_t)ev.time_us(i) - __ldg(pl.w_start + w);
-    uint32_t z = 0, d = 0;
-    if (dt > 0) {
-        uint32_t u = dt > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)dt;
-        z = pl.div_abin.div(u);
-        if (z > (uint32_t)(nb - 1)) z = nb - 1;      // inclusive right edge of the last bin
-        uint32_t rem = u - z * pl.abin;
-        d = rem > kDMax ? kDMax : rem;
-    }
-    uint32_t pix = (uint32_t)e.y * pl.W + e.x;
-    uint32_t tile = pl.div_P.div(pix);
-    c.tile = (int)tile;
-    c.gbin = __ldg(pl.w_binbase + w) + (int)z;
-    c.rec = (d << 14) | ((pix - tile * pl.P) << 1) | (uint32_t)e.p;
-    c.ok = true;
-    return c;
+__device__ __forceinline__ WinInfo load_window(const StreamPlan& pl, int w) {
+    WinInfo wi;
+    wi.begin = pl.w_begin[w]; wi.end = pl.w_end[w]; wi.start = pl.w_start[w];
+    wi.nbins = pl.w_nbins[w]; wi.binbase = pl.w_binbase[w];
+    return wi;
 }
 
 // First window whose event range ends after event index i.
@@ -123,90 +103,207 @@ __device__ __forceinline__ int first_window(const StreamPlan& pl, int64_t i) {
     return lo;
 }
 
-// Chunk prologue shared by the count and scatter passes: window of the first event and
-// the first global bin the chunk can touch.
-__device__ __forceinline__ void chunk_origin(const SoA& ev, const StreamPlan& pl, int64_t c0, int64_t c1,
-                                             int& w0, int& gb0) {
-    w0 = first_window(pl, c0);
-    gb0 = 0;
-    if (w0 < pl.n_windows) {
-        int64_t i = c0 > pl.w_begin[w0] ? c0 : pl.w_begin[w0];
-        gb0 = pl.w_binbase[w0];
-        if (i < c1 && i < pl.w_end[w0]) {
-            int64_t dt = (int64_t)ev.t[i] - pl.w_start[w0];
-            if (dt > 0) {
-                uint32_t z = pl.div_abin.div(dt > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)dt);
-                int nb = pl.w_nbins[w0];
-                if ((int)z > nb - 1) z = nb > 0 ? nb - 1 : 0;
-                gb0 += (int)z;
-            }
-        }
+// Bin of a timestamp inside window `wi` and the offset d from the bin start:
+// z = clamp(floor((t - start) / abin), 0, nbins - 1) -- inclusive edges, later bin wins
+// (generate_taf.py:201-202) -- and d = t - (start + z abin), saturated to 18 bits.
+__device__ __forceinline__ void bin_of(const StreamPlan& pl, const WinInfo& wi, uint32_t t, uint32_t& z, uint32_t& d) {
+    const int64_t dt = (int64_t)t - wi.start;
+    z = 0; d = 0;
+    if (dt > 0) {
+        const uint32_t u = dt > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)dt;
+        z = pl.div_abin.div(u);
+        if (z > (uint32_t)(wi.nbins - 1)) z = wi.nbins - 1;
+        const uint32_t rem = u - z * pl.abin;
+        d = rem > kDMax ? kDMax : rem;
     }
 }
 
-template <bool kScatter>
-__global__ void __launch_bounds__(kBucketThreads)
-taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last) {
-    extern __shared__ uint32_t hist[];            // [kLocalBins][n_tiles]
-    __shared__ int s_w0, s_gb0;
-    const int nh = kLocalBins * pl.n_tiles;
-    for (int i = threadIdx.x; i < nh; i += kBucketThreads) hist[i] = 0;
-    const int64_t c0 = ev_first + (int64_t)blockIdx.x * (kBucketThreads * kBucketPerThread);
-    const int64_t c1 = min(c0 + kBucketThreads * kBucketPerThread, ev_last);
-    if (threadIdx.x == 0) {
-        int w0, gb0;
-        chunk_origin(ev, pl, c0, c1, w0, gb0);
-        s_w0 = w0; s_gb0 = gb0;
+// Block-wide exclusive scan of n <= kBucketThreads * 16 shared-memory counters.
+// Returns the total.  `tmp` holds one word per warp (+1).
+__device__ __forceinline__ uint32_t block_exclusive_scan(const uint32_t* in, uint32_t* out, int n, uint32_t* tmp) {
+    const int per = (n + kBucketThreads - 1) / kBucketThreads;
+    const int lo = threadIdx.x * per, hi = min(lo + per, n);
+    uint32_t mine = 0;
+    for (int i = lo; i < hi; ++i) mine += in[i];
+    uint32_t incl = mine;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) tmp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < kBucketThreads / 32 ? tmp[lane] : 0u, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        if (lane < kBucketThreads / 32) tmp[lane] = wi - w;
+        if (lane == kBucketThreads / 32 - 1) tmp[kBucketThreads / 32] = wi;
     }
     __syncthreads();
-    const int gb0 = s_gb0;
-    int w = s_w0;
+    uint32_t run = tmp[wid] + incl - mine;
+    for (int i = lo; i < hi; ++i) { const uint32_t c = in[i]; out[i] = run; run += c; }
+    return tmp[kBucketThreads / 32];
+}
 
-    int key[kBucketPerThread];          // >= 0: smem slot, -1: dropped, -2: out of the local bins
-    uint32_t rank[kBucketPerThread], rec[kBucketPerThread];
-    int far_idx[kBucketPerThread];
-#pragma unroll
-    for (int k = 0; k < kBucketPerThread; ++k) {
-        const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
-        key[k] = -1;
-        if (i >= c1) continue;
-        Classified c = classify(ev, pl, i, w);
-        if (!c.ok) continue;
-        rec[k] = c.rec;
-        const int lb = c.gbin - gb0;
-        if (lb >= 0 && lb < kLocalBins) {
-            key[k] = lb * pl.n_tiles + c.tile;
-            rank[k] = atomicAdd(&hist[key[k]], 1u);
-        } else {                          // unsorted input or a very sparse stream
-            key[k] = -2;
-            far_idx[k] = c.tile * pl.TB + c.gbin;
-            if (!kScatter) { atomicAdd(pl.counts + far_idx[k], 1u); pl.bin_any[c.gbin] = 1u; }
-        }
+// Shared-memory carve-up of the bucketing kernels.
+struct BucketSmem {
+    int lutx, luty, hist, loff, gbase, sorted, skey, total;
+    __host__ __device__ BucketSmem(int lut_w, int lut_h, int nh, bool scatter) {
+        int o = 0;
+        lutx = o;  o += (lut_w * 2 + 15) / 16 * 16;
+        luty = o;  o += (lut_h * 2 + 15) / 16 * 16;
+        hist = o;  o += nh * 4;
+        loff = o;  o += scatter ? nh * 4 : 0;
+        gbase = o; o += scatter ? nh * 4 : 0;
+        sorted = o; o += scatter ? kBucketThreads * kBucketPerThread * 4 : 0;
+        skey = o;  o += scatter ? kBucketThreads * kBucketPerThread * 2 : 0;
+        total = (o + 15) / 16 * 16;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nh; i += kBucketThreads) {
-        const uint32_t c = hist[i];
-        if (!c) continue;
-        const int lb = i / pl.n_tiles, tile = i - lb * pl.n_tiles, gbin = gb0 + lb;
+};
+
+// Bucketing passes.  Persistent CTAs walk 4096-event chunks of the time-ordered stream.
+//  count   (kScatter = false): per-chunk shared-memory histogram over (local bin, tile),
+//          flushed with one global atomic per non-empty counter; sets the per-bin flags.
+//  scatter (kScatter = true):  the same histogram with ranks, a block scan, one global
+//          reservation per non-empty counter, then the chunk's records are ordered in shared
+//          memory so that each (tile, bin) run is written with consecutive addresses.
+template <bool kScatter>
+__global__ void __launch_bounds__(kBucketThreads, 2)
+taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, int lut_w, int lut_h) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    const int nh = kLocalBins * pl.n_tiles;
+    const bool use_lut = ev.xmap != nullptr && ev.ymap != nullptr;
+    const BucketSmem lay(use_lut ? lut_w : 0, use_lut ? lut_h : 0, nh, kScatter);
+    uint16_t* s_lutx = reinterpret_cast<uint16_t*>(bsm + lay.lutx);
+    uint16_t* s_luty = reinterpret_cast<uint16_t*>(bsm + lay.luty);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(bsm + lay.hist);
+    uint32_t* loff = reinterpret_cast<uint32_t*>(bsm + lay.loff);
+    uint32_t* gbase = reinterpret_cast<uint32_t*>(bsm + lay.gbase);
+    uint32_t* sorted = reinterpret_cast<uint32_t*>(bsm + lay.sorted);
+    uint16_t* skey = reinterpret_cast<uint16_t*>(bsm + lay.skey);
+    __shared__ WinInfo s_win;
+    __shared__ int s_w0, s_gb0, s_single;
+    __shared__ uint32_t s_tmp[kBucketThreads / 32 + 1];
+
+    if (use_lut) {
+        for (int i = threadIdx.x; i < lut_w; i += kBucketThreads) s_lutx[i] = ev.xmap[i];
+        for (int i = threadIdx.x; i < lut_h; i += kBucketThreads) s_luty[i] = ev.ymap[i];
+    }
+    const uint32_t W = pl.W, H = pl.H;
+
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t c0 = ev_first + (int64_t)chunk * (kBucketThreads * kBucketPerThread);
+        const int64_t c1 = min(c0 + kBucketThreads * kBucketPerThread, ev_last);
+        __syncthreads();                                   // previous chunk is done with smem
+        for (int i = threadIdx.x; i < nh; i += kBucketThreads) hist[i] = 0;
+        if (threadIdx.x == 0) {
+            const int w0 = first_window(pl, c0);
+            int gb0 = 0, single = 0;
+            if (w0 < pl.n_windows) {
+                const WinInfo wi = load_window(pl, w0);
+                s_win = wi;
+                single = (c0 >= wi.begin && c1 <= wi.end && wi.nbins > 0) ? 1 : 0;
+                const int64_t i = c0 > wi.begin ? c0 : wi.begin;
+                gb0 = wi.binbase;
+                if (i < c1 && i < wi.end && wi.nbins > 0) {
+                    uint32_t z, d;
+                    bin_of(pl, wi, ev.t[i], z, d);
+                    gb0 += (int)z;
+                }
+            }
+            s_w0 = w0; s_gb0 = gb0; s_single = single;
+        }
+        __syncthreads();
+        const int gb0 = s_gb0;
+        const bool single = s_single != 0;
+        int w = s_w0;
+        WinInfo wi = s_win;
+
+        // all global loads of the chunk are issued before any of them is used
+        uint32_t tt[kBucketPerThread];
+        uint16_t xr[kBucketPerThread], yr[kBucketPerThread];
+        uint8_t pr[kBucketPerThread];
+#pragma unroll
+        for (int k = 0; k < kBucketPerThread; ++k) {
+            const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
+            if (i < c1) { tt[k] = __ldg(ev.t + i); xr[k] = __ldg(ev.x + i); yr[k] = __ldg(ev.y + i); pr[k] = __ldg(ev.p + i); }
+        }
+
+        // per event: (smem counter << 12) | rank inside the chunk, or kNone when dropped
+        constexpr uint32_t kNone = 0xFFFFFFFFu;
+        uint32_t slot[kBucketPerThread], rec[kBucketPerThread];
+#pragma unroll
+        for (int k = 0; k < kBucketPerThread; ++k) {
+            const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
+            slot[k] = kNone;
+            if (i >= c1) continue;
+            if (!single) {                  // chunk straddles a window boundary or a gap
+                while (w < pl.n_windows && i >= __ldg(pl.w_end + w)) ++w;
+                if (w >= pl.n_windows) continue;
+                wi = load_window(pl, w);
+                if (i < wi.begin || wi.nbins <= 0) continue;
+            }
+            uint32_t xm = xr[k], ym = yr[k];
+            bool ok = pr[k] < 2;
+            if (use_lut) {
+                ok = ok && xm < (uint32_t)lut_w && ym < (uint32_t)lut_h;
+                xm = s_lutx[ok ? xm : 0]; ym = s_luty[ok ? ym : 0];
+            }
+            ok = ok && xm < W && ym < H;
+            if (!ok) continue;
+            uint32_t z, d;
+            bin_of(pl, wi, tt[k], z, d);
+            const uint32_t pix = ym * W + xm;
+            const uint32_t tile = pl.div_P.div(pix);
+            rec[k] = (d << 14) | ((pix - tile * pl.P) << 1) | pr[k];
+            const int gbin = wi.binbase + (int)z;
+            const int lb = gbin - gb0;
+            if (lb >= 0 && lb < kLocalBins) {
+                const uint32_t key = (uint32_t)(lb * pl.n_tiles) + tile;
+                if (kScatter) slot[k] = (key << 12) | atomicAdd(&hist[key], 1u);
+                else atomicAdd(&hist[key], 1u);
+            } else {                          // unsorted input or a very sparse stream: go straight to global
+                uint32_t* cursor = pl.counts + (int64_t)tile * pl.TB + gbin;
+                if (kScatter)
+                    pl.records[pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] + atomicAdd(cursor, 1u)] = rec[k];
+                else { atomicAdd(cursor, 1u); pl.bin_any[gbin] = 1u; }
+            }
+        }
+        __syncthreads();
         if (!kScatter) {
-            atomicAdd(pl.counts + (int64_t)tile * pl.TB + gbin, c);
-            pl.bin_any[gbin] = 1u;
-        } else {
-            hist[i] = pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] +
-                      atomicAdd(pl.counts + (int64_t)tile * pl.TB + gbin, c);
+            for (int i = threadIdx.x; i < nh; i += kBucketThreads) {
+                const uint32_t c = hist[i];
+                if (!c) continue;
+                const int lb = i / pl.n_tiles, tile = i - lb * pl.n_tiles, gbin = gb0 + lb;
+                atomicAdd(pl.counts + (int64_t)tile * pl.TB + gbin, c);
+                pl.bin_any[gbin] = 1u;
+            }
+            continue;
         }
-    }
-    if (!kScatter) return;
-    __syncthreads();
+        const uint32_t n_valid = block_exclusive_scan(hist, loff, nh, s_tmp);
+        for (int i = threadIdx.x; i < nh; i += kBucketThreads) {
+            const uint32_t c = hist[i];
+            if (!c) continue;
+            const int lb = i / pl.n_tiles, tile = i - lb * pl.n_tiles, gbin = gb0 + lb;
+            gbase[i] = pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] +
+                       atomicAdd(pl.counts + (int64_t)tile * pl.TB + gbin, c) - loff[i];
+        }
 #pragma unroll
-    for (int k = 0; k < kBucketPerThread; ++k) {
-        if (key[k] >= 0) {
-            pl.records[hist[key[k]] + rank[k]] = rec[k];
-        } else if (key[k] == -2) {
-            const int tile = far_idx[k] / pl.TB, gbin = far_idx[k] - tile * pl.TB;
-            pl.records[pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] +
-                       atomicAdd(pl.counts + far_idx[k], 1u)] = rec[k];
+        for (int k = 0; k < kBucketPerThread; ++k) {
+            if (slot[k] == kNone) continue;
+            const uint32_t key = slot[k] >> 12;
+            const uint32_t pos = loff[key] + (slot[k] & 0xFFFu);
+            sorted[pos] = rec[k];
+            skey[pos] = (uint16_t)key;
         }
+        __syncthreads();
+        for (uint32_t pos = threadIdx.x; pos < n_valid; pos += kBucketThreads)
+            pl.records[gbase[skey[pos]] + pos] = sorted[pos];
     }
 }
 
@@ -411,16 +508,17 @@ taf_tile_kernel(TileParams tp) {
     int ready_chunk = -1;      // highest chunk this thread has observed complete
     int next_refill = kStages; // next chunk to load; its stage is free once chunk (next_refill - kStages) is drained
     bool staged_once = false;
+    // batch descriptors are fetched two batches ahead, their offsets / flags one batch ahead
+    Batch nmeta = pl.batches[pl.n_batches > 1 ? 1 : 0];
     for (int j = 0; j < pl.n_batches; ++j) {
         const int buf = j & 1;
         const Batch meta = s_meta[buf];
-        // prefetch the next batch's offsets / flags (latency hidden behind this batch)
-        Batch nmeta = meta;
         uint32_t pre_off = 0, pre_any = 0;
+        Batch nnmeta = nmeta;
         if (j + 1 < pl.n_batches) {
-            nmeta = pl.batches[j + 1];
             if (tid <= nmeta.nb) pre_off = my_off[nmeta.gbin0 + tid];
             if (tid < nmeta.nb) pre_any = pl.bin_any[nmeta.gbin0 + tid];
+            if (j + 2 < pl.n_batches) nnmeta = pl.batches[j + 2];
         }
         if (meta.flags & 1) {
 #pragma unroll
@@ -544,6 +642,7 @@ taf_tile_kernel(TileParams tp) {
             if (tid == 0) s_meta[nb] = nmeta;
             if (tid <= nmeta.nb) s_off[nb * (kBatchBins + 1) + tid] = pre_off;
             if (tid < nmeta.nb) s_any[nb * kBatchBins + tid] = pre_any;
+            nmeta = nnmeta;
         }
         __syncthreads();
     }
@@ -629,11 +728,14 @@ int64_t evrep_taf_stream_scratch_bytes(int64_t n_events, int n_windows, int64_t 
 
 int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
                      const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W, int K,
-                     const uint16_t* xmap, const uint16_t* ymap, float* state_inout, int emit_state_every_window,
+                     const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                     float* state_inout, int emit_state_every_window,
                      float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
                      void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream) {
     if (n_events < 0 || n_windows < 0 || H <= 0 || W <= 0 || abin <= 0 || !state_inout || !scratch) return EVREP_ERR_ARG;
     if (K != 4 && K != 8) return EVREP_ERR_ARG;
+    if (xmap && ymap && (sensor_h <= 0 || sensor_w <= 0 || sensor_h > EVREP_COORD_LUT_LEN || sensor_w > EVREP_COORD_LUT_LEN))
+        return EVREP_ERR_ARG;
     if ((uint32_t)abin > kDMax) return EVREP_ERR_RANGE;
     if (n_windows == 0) return EVREP_OK;
     if (!windows_host || !out || (n_events > 0 && (!t || !x || !y || !p))) return EVREP_ERR_ARG;
@@ -722,11 +824,18 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
         EVREP_CUDA(cudaMemsetAsync(s + L.o_counts, 0, (size_t)(L.o_offrel - L.o_counts), st));   // counts + bin_any
         const int64_t ev_first = windows_host[0].ev_begin, ev_last = windows_host[n_windows - 1].ev_end;
         const int64_t per_cta = kBucketThreads * kBucketPerThread;
-        const int64_t grid = (ev_last - ev_first + per_cta - 1) / per_cta;
-        const size_t hist_bytes = (size_t)kLocalBins * L.n_tiles * sizeof(uint32_t);
+        const int64_t n_chunks = (ev_last - ev_first + per_cta - 1) / per_cta;
+        if (n_chunks >= (1ll << 31)) return EVREP_ERR_RANGE;
+        const int grid = (int)(n_chunks < 2ll * sm_count() ? n_chunks : 2ll * sm_count());
+        const bool use_lut = xmap && ymap;
+        const int nh = kLocalBins * L.n_tiles;
+        const size_t smem_count = (size_t)BucketSmem(use_lut ? sensor_w : 0, use_lut ? sensor_h : 0, nh, false).total;
+        const size_t smem_scatter = (size_t)BucketSmem(use_lut ? sensor_w : 0, use_lut ? sensor_h : 0, nh, true).total;
+        EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+        EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
         SoA ev{t, x, y, p, xmap, ymap};
         if (grid > 0) {
-            taf_bucket_kernel<false><<<(unsigned)grid, kBucketThreads, hist_bytes, st>>>(ev, pl, ev_first, ev_last);
+            taf_bucket_kernel<false><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h);
             EVREP_LAUNCH_CHECK();
         }
         taf_scan_rows_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
@@ -734,7 +843,7 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
         taf_scan_tiles_kernel<<<1, 1024, 0, st>>>(pl);
         EVREP_LAUNCH_CHECK();
         if (grid > 0) {
-            taf_bucket_kernel<true><<<(unsigned)grid, kBucketThreads, hist_bytes, st>>>(ev, pl, ev_first, ev_last);
+            taf_bucket_kernel<true><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h);
             EVREP_LAUNCH_CHECK();
         }
     } else {

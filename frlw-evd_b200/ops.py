@@ -39,6 +39,7 @@ class CoordMaps:
     """Device LUTs for the gen4 down-scaling policy (``generate_taf.py:103-104,216-218``)."""
     xmap: torch.Tensor      # u16 [16384]
     ymap: torch.Tensor
+    sensor_shape: tuple = (COORD_LUT_LEN, COORD_LUT_LEN)   # raw (H, W) range the maps cover
 
 
 def make_coord_maps(sensor_shape, target_shape, device) -> CoordMaps:
@@ -52,7 +53,7 @@ def make_coord_maps(sensor_shape, target_shape, device) -> CoordMaps:
         full[:n_in] = (np.arange(n_in, dtype=np.float64) * ratio).astype(np.int64).astype(np.uint16)
         return torch.from_numpy(full).to(device)
 
-    return CoordMaps(xmap=lut(W, rw), ymap=lut(H, rh))
+    return CoordMaps(xmap=lut(W, rw), ymap=lut(H, rh), sensor_shape=(H, W))
 
 
 def nearest_maps(in_shape, out_shape, device):
@@ -300,7 +301,7 @@ def taf_bin_aos64(events, shape, K: int, state):
 
 
 def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=None,
-               emit_state_every_window=True, out=None, tile_events=None):
+               emit_state_every_window=False, out=None, tile_events=None):
     """T2: run a list of windows ``(ev_begin, ev_end, start_time, n_bins, fresh)`` through
     the bucketing pass and the persistent tile kernel.  ``state`` (f32 ``[H,W,2,K]``) is
     updated IN PLACE.  Returns f32 ``[n_windows, 2K, H, W]``.  ``tile_events``: optional pair
@@ -322,7 +323,8 @@ def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=N
     buf = workspace("taf_stream", need, ev.device)
     xm, ym = _maps(maps)
     _lib.call("evrep_taf_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
-              ctypes.cast(arr, ctypes.c_void_p), nw, int(abin), H, W, K, xm, ym, _ptr(state),
+              ctypes.cast(arr, ctypes.c_void_p), nw, int(abin), H, W, K, xm, ym,
+              maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W, _ptr(state),
               int(bool(emit_state_every_window)), _ptr(out), 2 * K * H * W, _ptr(buf), buf.numel(),
               _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
     return out

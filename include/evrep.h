@@ -149,8 +149,12 @@ int evrep_taf_bin_aos64(const double* events, int64_t n, int ncols, int H, int W
  * reference's sequential float32 sum to rounding (bit-exact for n == 1).
  *
  * out: f32 [n_windows][2K,H,W] (window w at out + w * out_stride floats).
- * state_inout: f32 [H,W,2,K]; read unless windows[0].fresh, written after the last window
- * (and after every window when emit_state_every_window != 0).
+ * state_inout: f32 [H,W,2,K]; read unless windows[0].fresh, written after the last window.
+ * The state after window w is, by definition, the [H,W,2,K] permutation of out[w]
+ * (generate_taf.py:55), so nothing is lost by keeping it on chip in between; pass
+ * emit_state_every_window != 0 to have the tensor rewritten after every window anyway.
+ * sensor_h / sensor_w: raw coordinate range covered by ymap / xmap (ignored when the maps
+ * are NULL); raw coordinates beyond it are dropped.
  * K must be 4 or 8; abin <= 262143; at most 2048 tiles of 2304 pixels.
  * ev_tiles_begin / ev_tiles_end: optional cudaEvent_t handles recorded on `stream` right
  * before / after the tile kernel (the dominant launch), for live roofline timing. */
@@ -166,7 +170,7 @@ int64_t evrep_taf_stream_scratch_bytes(int64_t n_events, int n_windows, int64_t 
 int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
                      int64_t n_events, const evrep_taf_window* windows_host, int n_windows,
                      int abin, int H, int W, int K,
-                     const uint16_t* xmap, const uint16_t* ymap,
+                     const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
                      float* state_inout, int emit_state_every_window,
                      float* out, int64_t out_stride,
                      void* scratch, int64_t scratch_bytes,

@@ -48,7 +48,7 @@ def test_small_grid_mixed_windows(K):
     want, want_state = oracle_taf_windows(t, x, y, p, windows, abin, (H, W), K)
     ev = ops.EventStream.from_numpy(t, x, y, p)
     state = ops.taf_fresh_state((H, W), K, DEV)
-    got = ops.taf_stream(ev, windows, abin, (H, W), K, state)
+    got = ops.taf_stream(ev, windows, abin, (H, W), K, state, emit_state_every_window=(K == 4))
     for i in range(len(windows)):
         assert close(got[i], want[i]), i
     assert close(state, want_state)
