@@ -147,7 +147,9 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(const uint32_t* in, uin
     __syncthreads();
     uint32_t run = tmp[wid] + incl - mine;
     for (int i = lo; i < hi; ++i) { const uint32_t c = in[i]; out[i] = run; run += c; }
-    return tmp[kBucketThreads / 32];
+    const uint32_t total = tmp[kBucketThreads / 32];
+    __syncthreads();                     // `out` is complete (and `tmp` reusable) for every thread
+    return total;
 }
 
 // Shared-memory carve-up of the bucketing kernels.

@@ -97,3 +97,25 @@ def test_gen4_policy_recording(tmp_path):
         out, s2 = ops.taf_bin(rec.events.slice(max(lo, w0[0]), min(hi, w0[1])), w0[2] + b * 10000, 10000 + 1e-8,
                               (512, 640), 8, s2, geom.coord_maps)
     assert close(out, got[0])
+
+
+def test_many_chunks_per_bucketing_cta_matches_bin_by_bin():
+    """3 M events: more 4096-event chunks than bucketing CTAs (persistent loop), checked
+    against the independent bin-by-bin CUDA path (oracle too slow at this size)."""
+    t, x, y, p = synth.make_stream(720, 1280, 300000, 1e7, 77)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    maps = ops.make_coord_maps((720, 1280), (512, 640), DEV)
+    windows, prev = [], 0
+    for end in (100000, 150000, 200000, 250000, 300000):
+        windows.append((idx(t, prev), idx(t, end), prev, (end - prev) // 10000, int(prev == 0)))
+        prev = end
+    state = ops.taf_fresh_state((512, 640), 8, DEV)
+    got = ops.taf_stream(ev, windows, 10000, (512, 640), 8, state, maps)
+    s2 = ops.taf_fresh_state((512, 640), 8, DEV)
+    for b in range(30):
+        lo, hi = idx(t, b * 10000), idx(t, (b + 1) * 10000)
+        out, s2 = ops.taf_bin(ev.slice(lo, hi), b * 10000, 10000 + 1e-8, (512, 640), 8, s2, maps, in_place=True)
+        if (b + 1) * 10000 in (100000, 150000, 200000, 250000, 300000):
+            w = [100000, 150000, 200000, 250000, 300000].index((b + 1) * 10000)
+            assert close(got[w], out), w
+    assert close(state, s2)
