@@ -239,34 +239,12 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
         // per event: (smem counter << 12) | rank inside the chunk, or kNone when dropped
         constexpr uint32_t kNone = 0xFFFFFFFFu;
         uint32_t slot[kBucketPerThread], rec[kBucketPerThread];
-#pragma unroll
-        for (int k = 0; k < kBucketPerThread; ++k) {
-            const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
-            slot[k] = kNone;
-            if (i >= c1) continue;
-            if (!single) {                  // chunk straddles a window boundary or a gap
-                while (w < pl.n_windows && i >= __ldg(pl.w_end + w)) ++w;
-                if (w >= pl.n_windows) continue;
-                wi = load_window(pl, w);
-                if (i < wi.begin || wi.nbins <= 0) continue;
-            }
-            uint32_t xm = xr[k], ym = yr[k];
-            bool ok = pr[k] < 2;
-            if (use_lut) {
-                ok = ok && xm < (uint32_t)lut_w && ym < (uint32_t)lut_h;
-                xm = s_lutx[ok ? xm : 0]; ym = s_luty[ok ? ym : 0];
-            }
-            ok = ok && xm < W && ym < H;
-            if (!ok) continue;
-            uint32_t z, d;
-            bin_of(pl, wi, tt[k], z, d);
-            const uint32_t pix = ym * W + xm;
-            const uint32_t tile = pl.div_P.div(pix);
-            rec[k] = (d << 14) | ((pix - tile * pl.P) << 1) | pr[k];
-            const int gbin = wi.binbase + (int)z;
-            const int lb = gbin - gb0;
-            if (lb >= 0 && lb < kLocalBins) {
-                const uint32_t key = (uint32_t)(lb * pl.n_tiles) + tile;
+
+        // count / rank one classified event
+        auto deposit = [&](int k, uint32_t tile, int gbin) {
+            const uint32_t lb = (uint32_t)(gbin - gb0);
+            if (lb < (uint32_t)kLocalBins) {
+                const uint32_t key = lb * (uint32_t)pl.n_tiles + tile;
                 if (kScatter) slot[k] = (key << 12) | atomicAdd(&hist[key], 1u);
                 else atomicAdd(&hist[key], 1u);
             } else {                          // unsorted input or a very sparse stream: go straight to global
@@ -274,6 +252,57 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
                 if (kScatter)
                     pl.records[pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] + atomicAdd(cursor, 1u)] = rec[k];
                 else { atomicAdd(cursor, 1u); pl.bin_any[gbin] = 1u; }
+            }
+        };
+        // map raw coordinates to the grid; false when the event is to be dropped
+        auto locate = [&](int k, uint32_t& pix) -> bool {
+            uint32_t xm = xr[k], ym = yr[k];
+            bool ok = pr[k] < 2;
+            if (use_lut) {
+                ok = ok && xm < (uint32_t)lut_w && ym < (uint32_t)lut_h;
+                xm = s_lutx[min(xm, (uint32_t)lut_w - 1u)];
+                ym = s_luty[min(ym, (uint32_t)lut_h - 1u)];
+            }
+            pix = ym * W + xm;
+            return ok && xm < W && ym < H;
+        };
+
+        const bool fast = single && (c1 - c0) == kBucketThreads * kBucketPerThread &&
+                          wi.start >= 0 && wi.start <= 0xFFFFFFFFll;
+        if (fast) {
+            // the whole chunk lies in one window: 32-bit time arithmetic, no bounds checks
+            const uint32_t start32 = (uint32_t)wi.start, zmax = (uint32_t)(wi.nbins - 1);
+#pragma unroll
+            for (int k = 0; k < kBucketPerThread; ++k) {
+                slot[k] = kNone;
+                rec[k] = 0u;
+                uint32_t pix;
+                if (!locate(k, pix)) continue;
+                const uint32_t u = tt[k] >= start32 ? tt[k] - start32 : 0u;
+                const uint32_t z = min(pl.div_abin.div(u), zmax);
+                const uint32_t tile = pl.div_P.div(pix);
+                if (kScatter) rec[k] = (min(u - z * pl.abin, kDMax) << 14) | ((pix - tile * pl.P) << 1) | pr[k];
+                deposit(k, tile, wi.binbase + (int)z);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kBucketPerThread; ++k) {
+                const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
+                slot[k] = kNone;
+                if (i >= c1) continue;
+                if (!single) {                  // chunk straddles a window boundary or a gap
+                    while (w < pl.n_windows && i >= __ldg(pl.w_end + w)) ++w;
+                    if (w >= pl.n_windows) continue;
+                    wi = load_window(pl, w);
+                    if (i < wi.begin || wi.nbins <= 0) continue;
+                }
+                uint32_t pix;
+                if (!locate(k, pix)) continue;
+                uint32_t z, d;
+                bin_of(pl, wi, tt[k], z, d);
+                const uint32_t tile = pl.div_P.div(pix);
+                rec[k] = (d << 14) | ((pix - tile * pl.P) << 1) | pr[k];
+                deposit(k, tile, wi.binbase + (int)z);
             }
         }
         __syncthreads();
@@ -484,8 +513,10 @@ taf_tile_kernel(TileParams tp) {
         if (tid < m0.nb) s_any[tid] = pl.bin_any[m0.gbin0 + tid];
     }
 
-    // FIFO state of this thread's pixels: v[slot][polarity][k], k = K-1 newest
-    float v[SLOTS][2][K];
+    // FIFO state of this thread's pixels, as float2 pairs for the packed f32x2 adds of
+    // sm_100: element k of (slot, polarity) is v[s][p][k / 2].{x,y}; k = K-1 is the newest.
+    static_assert(K % 4 == 0, "K must be a multiple of 4");
+    float2 v[SLOTS][2][K / 2];
     const bool first_fresh = (pl.batches[0].flags & 1) != 0;
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
@@ -494,15 +525,15 @@ taf_tile_kernel(TileParams tp) {
             const float4* src = reinterpret_cast<const float4*>(tp.state + (pix0 + lp) * 2 * K);
 #pragma unroll
             for (int q = 0; q < 2 * K / 4; ++q) {
-                float4 f = src[q];
-                v[s][(q * 4) / K][(q * 4) % K + 0] = f.x; v[s][(q * 4) / K][(q * 4) % K + 1] = f.y;
-                v[s][(q * 4) / K][(q * 4) % K + 2] = f.z; v[s][(q * 4) / K][(q * 4) % K + 3] = f.w;
+                const float4 f = src[q];
+                v[s][(q * 4) / K][((q * 4) % K) / 2 + 0] = make_float2(f.x, f.y);
+                v[s][(q * 4) / K][((q * 4) % K) / 2 + 1] = make_float2(f.z, f.w);
             }
         } else {
 #pragma unroll
             for (int p = 0; p < 2; ++p)
 #pragma unroll
-                for (int k = 0; k < K; ++k) v[s][p][k] = kTafInit;
+                for (int k = 0; k < K / 2; ++k) v[s][p][k] = make_float2(kTafInit, kTafInit);
         }
     }
     __syncthreads();
@@ -528,7 +559,7 @@ taf_tile_kernel(TileParams tp) {
 #pragma unroll
                 for (int p = 0; p < 2; ++p)
 #pragma unroll
-                    for (int k = 0; k < K; ++k) v[s][p][k] = kTafInit;
+                    for (int k = 0; k < K / 2; ++k) v[s][p][k] = make_float2(kTafInit, kTafInit);
         }
         for (int b = 0; b < meta.nb; ++b) {
             const uint32_t o0 = s_off[buf * (kBatchBins + 1) + b], o1 = s_off[buf * (kBatchBins + 1) + b + 1];
@@ -564,28 +595,56 @@ taf_tile_kernel(TileParams tp) {
                     for (int r = next_refill; r < drained + kStages && r < n_chunks; ++r) issue(r);
                 if (drained + kStages > next_refill) next_refill = drained + kStages;
             }
+            const float2 minus1 = make_float2(-1.0f, -1.0f);
+            if (!have) {
+                // the tile saw nothing in this bin, but some other tile did: everything ages
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                const int lp = s * kTafThreads + tid;
-                if (lp >= npix) continue;
-                uint4 a = make_uint4(0u, 0u, 0u, 0u);
-                if (have) {
-                    a = *reinterpret_cast<uint4*>(acc + 2 * lp);              // {n0, S0, n1, S1}
-                    if (a.x | a.z) *reinterpret_cast<uint4*>(acc + 2 * lp) = make_uint4(0u, 0u, 0u, 0u);
-                }
-                const uint32_t nn[2] = {a.x, a.z}, ss[2] = {a.y, a.w};
+                for (int s = 0; s < SLOTS; ++s)
 #pragma unroll
-                for (int p = 0; p < 2; ++p) {
-                    // mean(t_norm) - 1 = S / (n * span) - 1 (generate_taf.py:23-27), branch free
-                    const bool active = nn[p] != 0u;
-                    const float denom = (float)(active ? nn[p] : 1u) * tp.span;
-                    const float mean = __fdividef((float)ss[p], denom) - 1.0f;
-                    float aged[K];
+                    for (int p = 0; p < 2; ++p)
 #pragma unroll
-                    for (int k = 0; k < K; ++k) aged[k] = v[s][p][k] - 1.0f;
+                        for (int k = 0; k < K / 2; ++k) v[s][p][k] = __fadd2_rn(v[s][p][k], minus1);
+            } else {
+                constexpr int G = SLOTS < 3 ? SLOTS : 3;            // accumulator loads in flight per group
 #pragma unroll
-                    for (int k = 0; k + 1 < K; ++k) v[s][p][k] = active ? aged[k + 1] : aged[k];
-                    v[s][p][K - 1] = active ? mean : aged[K - 1];
+                for (int g = 0; g < SLOTS; g += G) {
+                    uint4 a[G];
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        const int s = g + i;
+                        a[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (s >= SLOTS) continue;
+                        const int lp = s * kTafThreads + tid;
+                        // every slot but the last lies inside the tile's accumulator array
+                        if (s < SLOTS - 1 || lp < pl.P) {
+                            a[i] = *reinterpret_cast<uint4*>(acc + 2 * lp);       // {n0, S0, n1, S1}
+                            if (a[i].x | a[i].z) *reinterpret_cast<uint4*>(acc + 2 * lp) = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        const int s = g + i;
+                        if (s >= SLOTS) continue;
+                        const uint32_t nn[2] = {a[i].x, a[i].z}, ss[2] = {a[i].y, a[i].w};
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            // mean(t_norm) - 1 = S / (n span) - 1 (generate_taf.py:23-27); for n == 0
+                            // the value is NaN and is never selected
+                            const bool active = nn[p] != 0u;
+                            float r;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)nn[p] * tp.span));
+                            const float mean = fmaf((float)ss[p], r, -1.0f);
+                            float2 aged[K / 2];
+#pragma unroll
+                            for (int k = 0; k < K / 2; ++k) aged[k] = __fadd2_rn(v[s][p][k], minus1);
+#pragma unroll
+                            for (int k = 0; k < K / 2; ++k) {
+                                const float next = (k + 1 < K / 2) ? aged[k + 1].x : mean;
+                                v[s][p][k].x = active ? aged[k].y : aged[k].x;
+                                v[s][p][k].y = active ? next : aged[k].y;
+                            }
+                        }
+                    }
                 }
             }
             if (have) __syncthreads();                             // `acc` is clean again for the next bin
@@ -602,11 +661,14 @@ taf_tile_kernel(TileParams tp) {
 #pragma unroll
                 for (int s = 0; s < SLOTS; ++s) {
                     const int lp = s * kTafThreads + tid;
-                    if (lp >= npix) continue;
+                    if (s == SLOTS - 1 && lp >= pl.P) continue;     // columns >= npix are staged but never stored
 #pragma unroll
-                    for (int k = 0; k < K; ++k)
+                    for (int k = 0; k < K / 2; ++k)
 #pragma unroll
-                        for (int p = 0; p < 2; ++p) stage[(2 * k + p) * pl.P + lp] = v[s][p][k];
+                        for (int p = 0; p < 2; ++p) {
+                            stage[(4 * k + p) * pl.P + lp] = v[s][p][k].x;
+                            stage[(4 * k + 2 + p) * pl.P + lp] = v[s][p][k].y;
+                        }
                 }
                 fence_async_smem();
                 __syncthreads();
@@ -621,9 +683,12 @@ taf_tile_kernel(TileParams tp) {
                     const int lp = s * kTafThreads + tid;
                     if (lp >= npix) continue;
 #pragma unroll
-                    for (int k = 0; k < K; ++k)
+                    for (int k = 0; k < K / 2; ++k)
 #pragma unroll
-                        for (int p = 0; p < 2; ++p) __stcs(o + (int64_t)(2 * k + p) * HW + lp, v[s][p][k]);
+                        for (int p = 0; p < 2; ++p) {
+                            __stcs(o + (int64_t)(4 * k + p) * HW + lp, v[s][p][k].x);
+                            __stcs(o + (int64_t)(4 * k + 2 + p) * HW + lp, v[s][p][k].y);
+                        }
                 }
             }
             if (write_state) {
@@ -633,9 +698,10 @@ taf_tile_kernel(TileParams tp) {
                     if (lp >= npix) continue;
                     float4* dst = reinterpret_cast<float4*>(tp.state + (pix0 + lp) * 2 * K);
 #pragma unroll
-                    for (int q = 0; q < 2 * K / 4; ++q)
-                        dst[q] = make_float4(v[s][(q * 4) / K][(q * 4) % K + 0], v[s][(q * 4) / K][(q * 4) % K + 1],
-                                             v[s][(q * 4) / K][(q * 4) % K + 2], v[s][(q * 4) / K][(q * 4) % K + 3]);
+                    for (int q = 0; q < 2 * K / 4; ++q) {
+                        const float2 lo = v[s][(q * 4) / K][((q * 4) % K) / 2], hi = v[s][(q * 4) / K][((q * 4) % K) / 2 + 1];
+                        dst[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    }
                 }
             }
         }
