@@ -1,0 +1,95 @@
+"""Surface of Active Events -- drop-in for ``generate_surfaceofactiveevents.py``.
+
+``taf_cuda`` (the reference's name for the SAE kernel, :44-69), ``generate_leaky_cuda``
+(:71-80) and the Event Volume copy (:18-42) keep their signatures; the command line
+reproduces the driver (:82-220).
+
+The reference scatters timestamps with a non-accumulating ``index_put_`` whose result for
+duplicate pixels is unspecified on CUDA (and races across CPU threads); this library
+defines it as the maximum timestamp, i.e. the sequential result for time-sorted input.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+
+from . import ops
+from .recordings import DeviceRecording, Geometry, dump_u8, iter_recordings, parse_args
+
+LAMDAS = [0.00001, 0.0000025, 0.000001]            # :103
+TIME_WINDOW = [554126, 2216505, 5541263]           # :104 (timed sub-windows, test mode)
+EVENTS_WINDOW = 5000000                            # :106
+
+
+def generate_agile_event_volume_cuda(events, shape, events_window=50000, volume_bins=5):
+    """``generate_surfaceofactiveevents.py:18-42`` (Event Volume copy, returns the tensor only)."""
+    return ops.event_volume_aos64(events, tuple(shape), int(volume_bins))
+
+
+def taf_cuda(x, y, t, p, shape, lamdas, memory, now):
+    """``:44-69``: ``x, y, p`` integer tensors, ``t`` float32 timestamps.
+    Returns ``(f32 [2L,H,W], f32 memory [2,H,W], seconds)``."""
+    events = torch.stack([x.double(), y.double(), t.double(), p.double()], dim=1)
+    tick = time.time()
+    out, mem = ops.sae_aos64(events, tuple(shape), list(lamdas), memory, now)
+    torch.cuda.synchronize()
+    return out, mem, time.time() - tick
+
+
+def generate_leaky_cuda(events, shape, lamdas, memory, now):
+    """``:71-80``: float64 ``[N,4]`` (x, y, t, p); events outside the grid are dropped."""
+    tick = time.time()
+    out, mem = ops.sae_aos64(events, tuple(shape), list(lamdas), memory, now)
+    torch.cuda.synchronize()
+    return out, mem, time.time() - tick
+
+
+def encode_recording(rec: DeviceRecording, labels, geom: Geometry, mode="train"):
+    """Yield ``(label, u8 [L,2,Ht,Wt])`` (:147-213)."""
+    loader = rec.loader
+    t_upper, c_upper, memory = -100000000, 0, None
+    L = len(LAMDAS)
+    for label in labels:
+        end_time = int(label)
+        end_count = loader.seek_time(end_time)
+        if end_count is None:
+            continue
+        start_time = end_time - EVENTS_WINDOW
+        start_count = loader.seek_time(0 if start_time < 0 else start_time)
+        if start_count is None or start_time < 0:
+            start_count = 0
+        if start_time <= t_upper:
+            start_count = c_upper
+        t_upper, c_upper = label, end_count
+        keep = None
+        for tw in (TIME_WINDOW if mode == "test" else [max(TIME_WINDOW)]):
+            lo = loader.upper_index(end_time - tw, start_count, end_count)     # events[:, 2] > end_time - tw
+            vol, memory = ops.sae(rec.events.slice(lo, end_count), geom.grid, LAMDAS, memory, label, geom.coord_maps)
+            if tw == max(TIME_WINDOW):
+                keep = vol
+        u8 = ops.quantize_u8(geom.to_target(keep)).view(L, 2, geom.target[0], geom.target[1])
+        yield label, u8
+
+
+def main(argv=None):
+    args = parse_args("gen4", argv)
+    geom = Geometry.for_dataset(args.dataset)
+    total_time, total_count = 0.0, 0
+    for mode, name, event_file, labels in iter_recordings(args.raw_dir, args.label_dir):
+        rec = DeviceRecording(event_file)
+        torch.cuda.synchronize()
+        tick = time.time()
+        for label, u8 in encode_recording(rec, labels, geom, mode):
+            for j, lam in enumerate(LAMDAS):
+                dump_u8(u8[j], args.target_dir, "SurfaceOfActiveEvents{0}".format(lam), mode,
+                        name + "_" + str(label) + ".npy")
+            total_count += 1
+        if mode == "test":
+            total_time += time.time() - tick
+    if total_count and total_time:
+        print("Average Representation time: ", total_time / total_count)
+
+
+if __name__ == "__main__":
+    main()

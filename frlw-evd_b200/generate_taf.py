@@ -110,8 +110,8 @@ def encode_recording(rec: DeviceRecording, plan: List[TafWindow], geom: Geometry
             yield w.label, ops.taf_leaky_u8(vol, volume_bins, geom.target, geom.resize_maps)
 
 
-def main():
-    args = parse_args("gen4")
+def main(argv=None):
+    args = parse_args("gen4", argv)
     geom = Geometry.for_dataset(args.dataset)
     half = VOLUME_BINS // 2
     total_time, total_count = 0.0, 0

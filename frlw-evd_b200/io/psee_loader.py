@@ -111,11 +111,17 @@ class PSEELoader(object):
         return self._decode(lo, lo + ev_count)
 
     def load_delta_t(self, delta_t):
+        lo, hi = self.index_delta_t(delta_t)
+        return self._decode(lo, hi)
+
+    def index_delta_t(self, delta_t):
+        """``load_delta_t`` without the decode: advances the cursor / clock identically and
+        returns the event index range ``[lo, hi)`` it would have loaded."""
         if delta_t < 1:
             raise ValueError("load_delta_t(): delta_t must be at least 1 micro-second: {}".format(delta_t))
         if self.done or self._pos >= self._ev_count:
             self.done = True
-            return np.empty((0,), dtype=self._decode_dtype)
+            return self._pos, self._pos
         final_time = self.current_time + delta_t
         lo = self._pos
         hi = bisect.bisect_left(self._t, final_time, lo, self._ev_count)   # O(log n) probes of the map
@@ -125,7 +131,12 @@ class PSEELoader(object):
         self.current_time = final_time if last_seen >= final_time else last_seen + 1
         self._pos = hi
         self.done = self._pos >= self._ev_count
-        return self._decode(lo, hi)
+        return lo, hi
+
+    def upper_index(self, time_us, lo, hi):
+        """First index in ``[lo, hi)`` whose timestamp is ``> time_us`` (the drivers'
+        ``events[:, 2] > bound`` filters on time-sorted slices)."""
+        return bisect.bisect_right(self._t, time_us, lo, hi)
 
     def seek_event(self, ev_count):
         ev_count = int(ev_count)

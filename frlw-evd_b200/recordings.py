@@ -55,13 +55,13 @@ class Geometry:
         return volume if self.downscale else ops.nearest_resize(volume, self.target, self.resize_maps)
 
 
-def parse_args(default_dataset: str):
+def parse_args(default_dataset: str, argv=None):
     parser = argparse.ArgumentParser(description="event-representation generator (B200)")
     parser.add_argument("-raw_dir", type=str)      # "train, val, test" level directory of the event files
     parser.add_argument("-label_dir", type=str)    # "train, val, test" level directory of the annotations
     parser.add_argument("-target_dir", type=str)   # output directory
     parser.add_argument("-dataset", type=str, default=default_dataset)   # gen1 / gen4
-    return parser.parse_args()
+    return parser.parse_args(argv)
 
 
 def iter_recordings(raw_dir, label_dir):
