@@ -83,10 +83,10 @@ class DeviceRecording:
 
     def __init__(self, path: str, device="cuda"):
         self.loader = PSEELoader(path)
-        raw = torch.from_numpy(np.ascontiguousarray(self.loader.raw_bytes()))
-        if torch.device(device).type == "cuda":
-            raw = raw.pin_memory() if raw.numel() else raw
-        self.events = ops.decode_dat(raw.to(device, non_blocking=True))
+        payload = self.loader.raw_bytes()
+        staged = torch.empty(payload.shape[0], dtype=torch.uint8, pin_memory=payload.shape[0] > 0)
+        np.copyto(staged.numpy(), payload)               # file (page cache) -> pinned host memory, once
+        self.events = ops.decode_dat(staged.to(device, non_blocking=True))
 
 
 def dump_u8(tensor_u8: torch.Tensor, *path) -> None:
