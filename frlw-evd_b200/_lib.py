@@ -48,6 +48,13 @@ SIGNATURES = {
     "evrep_quantize_u8": (c_int, [P, c_int64, c_int, P, P]),
     "evrep_taf_leaky_u8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "evrep_leaky_transform": (c_int, [P, c_int64, P, P]),
+    "evrep_sparse_splat": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, P, P]),
+    "evrep_pixel_major_to_planar": (c_int, [P, c_int, c_int64, c_int, P, P]),
+    "evrep_sparse_agile_shift": (c_int, [P, P, c_int64, c_int, P, P]),
+    "evrep_sparse_taf": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P]),
+    "evrep_sparse_event_frame": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
+    "evrep_sparse_to_dense": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
+    "evrep_event_queue_tensor": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
 }
 
 _lib = None

@@ -193,6 +193,41 @@ int evrep_taf_leaky_u8(const float* volume, int K, int H, int W, int Ht, int Wt,
                        const int32_t* ysrc, const int32_t* xsrc, uint8_t* out, evrep_stream_t stream);
 int evrep_leaky_transform(const float* in, int64_t n, float* out, evrep_stream_t stream);
 
+/* ----------------------------------- S1-S6: data/sparse_ops.py (batched plugin surface) ----
+ * The reference's online encoders, called as `to_volume(events, B, shape, iter, memory,
+ * events_window, volume_bins, infer_time)` at data/fetcher.py:53.  `events` is the float64
+ * [N,5] matrix (b, x, y, t, p) ([N,7] (b, x, y, t, c, p, feature) for evrep_sparse_taf).
+ *
+ * evrep_sparse_splat: temporal bilinear splat with centres 0..C-1 into the pixel-major
+ *   accumulator acc f32 [B*H*W, C, 2] (zeroed by the call), slot 1-p.
+ *   mode 0: t* = (K t) / window             sparse_ops.py:12  (generate_agile_event_volume_cuda, full)
+ *   mode 1: t* = ((t - iter) + infer) / window * K      :15  (incremental, C = 2)
+ *   mode 2: t* = ((K - 1) t) / window                   :56  (generate_event_volume_cuda)
+ * evrep_pixel_major_to_planar: [B*HW, C2] -> [B, C2, HW]  (the permute(0,3,1,2,4) of :34,:68).
+ * evrep_sparse_agile_shift: :25-32 -- past[:, K-1] += fresh[:, 0] IN PLACE (the reference mutates
+ *   the caller's tensor), out_state = cat(past[:, 1:], fresh[:, 1:]).  Layouts [BHW, K, 2] / [BHW, 2, 2].
+ * evrep_sparse_taf: :72-85, out f32 [B, C, H, W, 2]; plane 1 becomes -1e8 where 0, +1 elsewhere.
+ * evrep_sparse_event_frame: :88-107, out f32 [B, 2, H, W], 255 where any event.
+ * evrep_sparse_to_dense: :109-121, locations int64 [N,3] (b, y, x), features f32 [N,C] -> [B,H,W,C]. */
+int evrep_sparse_splat(const double* events, int64_t n, int B, int H, int W, int C, int mode, float K,
+                       float window, float iter, float infer, float* acc, evrep_stream_t stream);
+int evrep_pixel_major_to_planar(const float* in, int B, int64_t HW, int C2, float* out, evrep_stream_t stream);
+int evrep_sparse_agile_shift(float* past, const float* fresh, int64_t BHW, int K, float* out_state,
+                             evrep_stream_t stream);
+int evrep_sparse_taf(const double* events, int64_t n, int B, int H, int W, int C, float* out, evrep_stream_t stream);
+int evrep_sparse_event_frame(const double* events, int64_t n, int B, int H, int W, float* out, evrep_stream_t stream);
+int evrep_sparse_to_dense(const int64_t* locations, const float* features, int64_t n, int B, int H, int W, int C,
+                          float* out, evrep_stream_t stream);
+
+/* -------------------- N1: data/event_representation_tool/src/event_queue_tensor.cpp:10-118 ----
+ * As the extension behaves (its deques are never fed during the event loop): every event
+ * (b, x, y, t, p, z) f32 [N,6] adds 1 - (start[b] + abin (z+1) - t) / abin to cell (p, b, y, x);
+ * positive totals land in queue slot Q-1 of plane 0, plane 1 is -1.  out f64 [2, Q, 2, B, H, W];
+ * totals: f32 [2*B*H*W] scratch. */
+int evrep_event_queue_tensor(const float* events, int64_t n, int Q, int B, int H, int W,
+                             const int32_t* start_times, int abin, float* totals, double* out,
+                             evrep_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
