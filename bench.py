@@ -244,20 +244,15 @@ def main():
     # end to end through the public call with host buffers
     e2e = None
     if not args.no_e2e:
+        from frlw_evd_b200 import generate_taf as gt
+        from frlw_evd_b200.recordings import Geometry
+        geom = Geometry((720, 1280), GRID, dev, coord_maps=maps)
         raw_host = torch.from_numpy(records.view(np.uint8)).pin_memory()
-        raw_dev = torch.empty_like(raw_host, device=dev)
-        u8_dev = torch.empty((nw, K, 2, GRID[0], GRID[1]), dtype=torch.uint8, device=dev)
-        u8_host = torch.empty(u8_dev.shape, dtype=torch.uint8).pin_memory()
-        dec = ops.EventStream.empty(n_events, dev)
-        st2 = ops.taf_fresh_state(GRID, K, dev)
+        pipe = gt.HostPipeline(geom, windows, K, ABIN, windows_per_chunk=24, device=dev)
+        u8_host = torch.empty(pipe.out_shape, dtype=torch.uint8).pin_memory()
 
         def e2e_step():
-            raw_dev.copy_(raw_host, non_blocking=True)
-            ops.decode_dat(raw_dev, dec)
-            ops.taf_stream(dec, windows, ABIN, GRID, K, st2, maps, False, out)
-            for w in range(nw):
-                ops.taf_leaky_u8(out[w], K, out=u8_dev[w])
-            u8_host.copy_(u8_dev, non_blocking=True)
+            pipe.run(raw_host, u8_host)
 
         e2e_step()
         barrier()
@@ -275,7 +270,8 @@ def main():
             e2e_ms = float(tmax[0])
         e2e = {"value": total_events / (e2e_ms * 1e-3) / 1e6, "unit": "Mevents/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(raw_host.numel()), "d2h_bytes_per_step": int(u8_host.numel()),
-               "path": "pinned .dat bytes -> H2D -> decode -> taf_stream -> leaky uint8 [K,2,Ht,Wt] -> D2H"}
+               "path": "pinned .dat bytes -> H2D -> decode -> taf_stream -> leaky uint8 [K,2,Ht,Wt] -> D2H, "
+                       "24-window chunks on three streams (generate_taf.HostPipeline)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

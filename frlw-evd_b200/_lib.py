@@ -47,6 +47,7 @@ SIGNATURES = {
     "evrep_nearest_resize": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "evrep_quantize_u8": (c_int, [P, c_int64, c_int, P, P]),
     "evrep_taf_leaky_u8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "evrep_taf_leaky_u8_batch": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "evrep_leaky_transform": (c_int, [P, c_int64, P, P]),
     "evrep_sparse_splat": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, P, P]),
     "evrep_pixel_major_to_planar": (c_int, [P, c_int, c_int64, c_int, P, P]),

@@ -309,19 +309,39 @@ leaky_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
 }
 
 // generate_taf.py:226-235: [2K,H,W] (channel 2k+p) -> u8 [K,2,Ht,Wt], slot axis flipped.
+// `n` windows at once: window w reads vol + w * vol_stride and writes out + w * 2K*Ht*Wt.
 __global__ void __launch_bounds__(kBlock)
-taf_leaky_u8_kernel(const float* __restrict__ vol, int K, int H, int W, int Ht, int Wt,
+taf_leaky_u8_kernel(const float* __restrict__ vol, int64_t vol_stride, int n, int K, int H, int W, int Ht, int Wt,
                     const int32_t* __restrict__ ysrc, const int32_t* __restrict__ xsrc, uint8_t* __restrict__ out) {
-    const int64_t total = (int64_t)2 * K * Ht * Wt;
+    const int64_t per = (int64_t)2 * K * Ht * Wt;
+    const int64_t total = per * n;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = !ysrc && !xsrc && (Wt % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(vol) & 15) == 0) && (vol_stride % 4 == 0);
+    if (vec) {          // same-size grid: 4 pixels per thread, 128-bit loads, 32-bit stores
+        for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total / 4; q += stride) {
+            const int64_t i = q * 4;
+            const int64_t w = i / per, j = i - w * per;
+            const int64_t plane = (int64_t)Ht * Wt;
+            const int ch = (int)(j / plane);
+            const int64_t pix = j - ch * plane;
+            const int k = K - 1 - (ch >> 1), p = ch & 1;
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(vol + w * vol_stride + (int64_t)(2 * k + p) * plane + pix));
+            const uint32_t packed = to_u8(leaky(v.x), 0) | (to_u8(leaky(v.y), 0) << 8) | (to_u8(leaky(v.z), 0) << 16) |
+                                    ((uint32_t)to_u8(leaky(v.w), 0) << 24);
+            reinterpret_cast<uint32_t*>(out)[q] = packed;
+        }
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        int X = (int)(i % Wt);
-        int64_t r = i / Wt;
+        const int64_t w = i / per, j = i - w * per;
+        int X = (int)(j % Wt);
+        int64_t r = j / Wt;
         int Y = (int)(r % Ht);
         int ch = (int)(r / Ht);                      // destination channel 2*slot + p
         int k = K - 1 - (ch >> 1), p = ch & 1;
         int ys = ysrc ? ysrc[Y] : Y, xs = xsrc ? xsrc[X] : X;
-        out[i] = to_u8(leaky(vol[((int64_t)(2 * k + p) * H + ys) * W + xs]), 0);
+        out[i] = to_u8(leaky(vol[w * vol_stride + ((int64_t)(2 * k + p) * H + ys) * W + xs]), 0);
     }
 }
 
@@ -553,7 +573,18 @@ int evrep_taf_leaky_u8(const float* volume, int K, int H, int W, int Ht, int Wt,
                        const int32_t* xsrc, uint8_t* out, evrep_stream_t stream) {
     if (!volume || !out || K <= 0 || H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0) return EVREP_ERR_ARG;
     if ((!ysrc || !xsrc) && (Ht != H || Wt != W)) return EVREP_ERR_ARG;
-    taf_leaky_u8_kernel<<<grid_for((int64_t)2 * K * Ht * Wt), kBlock, 0, as_stream(stream)>>>(volume, K, H, W, Ht, Wt, ysrc, xsrc, out);
+    taf_leaky_u8_kernel<<<grid_for((int64_t)2 * K * Ht * Wt), kBlock, 0, as_stream(stream)>>>(volume, 0, 1, K, H, W, Ht, Wt, ysrc, xsrc, out);
+    EVREP_LAUNCH_CHECK();
+    return EVREP_OK;
+}
+
+int evrep_taf_leaky_u8_batch(const float* volumes, int64_t volume_stride, int n_windows, int K, int H, int W, int Ht,
+                             int Wt, const int32_t* ysrc, const int32_t* xsrc, uint8_t* out, evrep_stream_t stream) {
+    if (!volumes || !out || n_windows < 0 || K <= 0 || H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0) return EVREP_ERR_ARG;
+    if ((!ysrc || !xsrc) && (Ht != H || Wt != W)) return EVREP_ERR_ARG;
+    if (n_windows == 0) return EVREP_OK;
+    taf_leaky_u8_kernel<<<grid_for((int64_t)2 * K * Ht * Wt * n_windows, 4), kBlock, 0, as_stream(stream)>>>(
+        volumes, volume_stride, n_windows, K, H, W, Ht, Wt, ysrc, xsrc, out);
     EVREP_LAUNCH_CHECK();
     return EVREP_OK;
 }

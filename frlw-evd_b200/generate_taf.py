@@ -110,6 +110,71 @@ def encode_recording(rec: DeviceRecording, plan: List[TafWindow], geom: Geometry
             yield w.label, ops.taf_leaky_u8(vol, volume_bins, geom.target, geom.resize_maps)
 
 
+class HostPipeline:
+    """End-to-end TAF encoding of one recording held in HOST memory: pinned ``.dat`` payload
+    in, pinned uint8 ``[n_windows, K, 2, Ht, Wt]`` out (the bytes of the ``bins*`` files).
+
+    The windows are processed in chunks; three streams overlap the host->device copy of
+    chunk c+1, the kernels of chunk c (decode, bucketing, tile kernel, fused
+    leaky/flip/resize/uint8 epilogue) and the device->host copy of chunk c-1.  The FIFO state
+    is carried between chunks in a device tensor."""
+
+    def __init__(self, geom: Geometry, plan, K=VOLUME_BINS, abin=ABIN, windows_per_chunk=24, device="cuda"):
+        self.geom, self.K, self.abin, self.device = geom, K, abin, torch.device(device)
+        self.windows = [w if isinstance(w, tuple) else w.as_tuple(abin) for w in plan]
+        self.chunks = [(i, min(i + windows_per_chunk, len(self.windows)))
+                       for i in range(0, len(self.windows), windows_per_chunk)]
+        max_ev = max((self.windows[b - 1][1] - self.windows[a][0] for a, b in self.chunks), default=0)
+        max_w = max((b - a for a, b in self.chunks), default=0)
+        H, W = geom.grid
+        Ht, Wt = geom.target
+        dev = self.device
+        self.raw = [torch.empty(max(max_ev, 1) * 8, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.soa = [ops.EventStream.empty(max(max_ev, 1), dev) for _ in range(2)]
+        self.vol = torch.empty((max(max_w, 1), 2 * K, H, W), dtype=torch.float32, device=dev)
+        self.u8 = [torch.empty((max(max_w, 1), K, 2, Ht, Wt), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.state = ops.taf_fresh_state(geom.grid, K, dev)
+        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.out_shape = (len(self.windows), K, 2, Ht, Wt)
+
+    def run(self, raw_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
+        """``raw_host``: pinned uint8 payload of the whole recording (8 bytes/event);
+        ``out_host``: pinned uint8 tensor of shape ``self.out_shape``."""
+        ev = torch.cuda.Event
+        in_done, raw_free, comp_done, out_done = ([ev() for _ in range(2)] for _ in range(4))
+        start = torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_comp, self.s_out):
+            s.wait_stream(start)
+        for c, (a, b) in enumerate(self.chunks):
+            k = c & 1
+            e0, e1 = self.windows[a][0], self.windows[b - 1][1]
+            n = e1 - e0
+            with torch.cuda.stream(self.s_in):
+                if c >= 2:
+                    self.s_in.wait_event(raw_free[k])
+                self.raw[k][:n * 8].copy_(raw_host[e0 * 8:e1 * 8], non_blocking=True)
+                in_done[k].record(self.s_in)
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(in_done[k])
+                soa = self.soa[k].slice(0, n)
+                ops.decode_dat(self.raw[k][:n * 8], soa)
+                raw_free[k].record(self.s_comp)
+                local = [(w[0] - e0, w[1] - e0, w[2], w[3], w[4]) for w in self.windows[a:b]]
+                vol = self.vol[:b - a]
+                ops.taf_stream(soa, local, self.abin, self.geom.grid, self.K, self.state, self.geom.coord_maps, False, vol)
+                if c >= 2:
+                    self.s_comp.wait_event(out_done[k])
+                ops.taf_leaky_u8_batch(vol, self.K, self.geom.target, self.geom.resize_maps, self.u8[k][:b - a])
+                comp_done[k].record(self.s_comp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(comp_done[k])
+                out_host[a:b].copy_(self.u8[k][:b - a], non_blocking=True)
+                out_done[k].record(self.s_out)
+        for s in (self.s_in, self.s_comp, self.s_out):
+            start.wait_stream(s)
+        return out_host
+
+
 def main(argv=None):
     args = parse_args("gen4", argv)
     geom = Geometry.for_dataset(args.dataset)

@@ -382,3 +382,19 @@ def taf_leaky_u8(volume, K: int, target_shape=None, maps=None, out=None):
     _lib.call("evrep_taf_leaky_u8", _ptr(volume.contiguous()), K, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
               _stream(volume.device))
     return out
+
+
+def taf_leaky_u8_batch(volumes, K: int, target_shape=None, maps=None, out=None):
+    """All windows of a ``taf_stream`` result at once: f32 ``[n,2K,H,W]`` -> u8 ``[n,K,2,Ht,Wt]``."""
+    _need_cuda(volumes)
+    n, C, H, W = volumes.shape
+    assert C == 2 * K and volumes.is_contiguous()
+    Ht, Wt = target_shape if target_shape is not None else (H, W)
+    if (Ht, Wt) != (H, W) and maps is None:
+        maps = nearest_maps((H, W), (Ht, Wt), volumes.device)
+    ys, xs = maps if maps is not None else (None, None)
+    if out is None:
+        out = torch.empty((n, K, 2, Ht, Wt), dtype=torch.uint8, device=volumes.device)
+    _lib.call("evrep_taf_leaky_u8_batch", _ptr(volumes), C * H * W, n, K, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
+              _stream(volumes.device))
+    return out

@@ -191,6 +191,10 @@ int evrep_nearest_resize(const float* in, int C, int H, int W, int Ht, int Wt,
 int evrep_quantize_u8(const float* in, int64_t n, int clamp255, uint8_t* out, evrep_stream_t stream);
 int evrep_taf_leaky_u8(const float* volume, int K, int H, int W, int Ht, int Wt,
                        const int32_t* ysrc, const int32_t* xsrc, uint8_t* out, evrep_stream_t stream);
+/* n_windows tensors at once: window w at volumes + w * volume_stride floats -> out + w * 2K*Ht*Wt. */
+int evrep_taf_leaky_u8_batch(const float* volumes, int64_t volume_stride, int n_windows, int K, int H, int W,
+                             int Ht, int Wt, const int32_t* ysrc, const int32_t* xsrc, uint8_t* out,
+                             evrep_stream_t stream);
 int evrep_leaky_transform(const float* in, int64_t n, float* out, evrep_stream_t stream);
 
 /* ----------------------------------- S1-S6: data/sparse_ops.py (batched plugin surface) ----

@@ -119,3 +119,24 @@ def test_many_chunks_per_bucketing_cta_matches_bin_by_bin():
             w = [100000, 150000, 200000, 250000, 300000].index((b + 1) * 10000)
             assert close(got[w], out), w
     assert close(state, s2)
+
+
+def test_host_pipeline_matches_single_launch(tmp_path):
+    """Chunked three-stream host pipeline == one launch + per-window epilogue."""
+    (t, x, y, p), labels = synth.write_recording(str(tmp_path), str(tmp_path), "train", "r", "gen1", 500000, 1e6, 11)
+    from frlw_evd_b200.recordings import DeviceRecording, Geometry
+    rec = DeviceRecording(str(tmp_path / "train" / "r_td.dat"))
+    geom = Geometry.for_dataset("gen1")
+    plan = gt.plan_windows(rec.loader, labels)
+    want = torch.stack([u8 for _, u8 in gt.encode_recording(rec, plan, geom)]).cpu()
+    raw = torch.from_numpy(np.array(rec.loader.raw_bytes())).pin_memory()
+    pipe = gt.HostPipeline(geom, plan, windows_per_chunk=3)
+    out = torch.empty(pipe.out_shape, dtype=torch.uint8).pin_memory()
+    pipe.run(raw, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    pipe2 = gt.HostPipeline(geom, plan, windows_per_chunk=100)      # one chunk
+    out2 = torch.empty(pipe2.out_shape, dtype=torch.uint8).pin_memory()
+    pipe2.run(raw, out2)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, want)
