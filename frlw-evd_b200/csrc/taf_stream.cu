@@ -152,6 +152,39 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(const uint32_t* in, uin
     return total;
 }
 
+// Per-chunk prologue of the bucketing passes, computed once by a tiny kernel: the window of
+// the chunk's first event, the first global bin the chunk can touch and whether the whole
+// chunk lies inside that window (the fast path).
+struct ChunkOrigin {
+    WinInfo win;
+    int w0, gb0, single, pad;
+};
+
+__global__ void __launch_bounds__(256)
+taf_chunk_origin_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, ChunkOrigin* __restrict__ origins) {
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= n_chunks) return;
+    const int64_t c0 = ev_first + (int64_t)chunk * (kBucketThreads * kBucketPerThread);
+    const int64_t c1 = min(c0 + kBucketThreads * kBucketPerThread, ev_last);
+    ChunkOrigin o;
+    o.w0 = first_window(pl, c0);
+    o.gb0 = 0; o.single = 0; o.pad = 0;
+    o.win.begin = o.win.end = o.win.start = 0; o.win.nbins = 0; o.win.binbase = 0;
+    if (o.w0 < pl.n_windows) {
+        const WinInfo wi = load_window(pl, o.w0);
+        o.win = wi;
+        o.single = (c0 >= wi.begin && c1 <= wi.end && wi.nbins > 0) ? 1 : 0;
+        const int64_t i = c0 > wi.begin ? c0 : wi.begin;
+        o.gb0 = wi.binbase;
+        if (i < c1 && i < wi.end && wi.nbins > 0) {
+            uint32_t z, d;
+            bin_of(pl, wi, ev.t[i], z, d);
+            o.gb0 += (int)z;
+        }
+    }
+    origins[chunk] = o;
+}
+
 // Shared-memory carve-up of the bucketing kernels.
 struct BucketSmem {
     int lutx, luty, hist, loff, gbase, sorted, skey, total;
@@ -176,7 +209,8 @@ struct BucketSmem {
 //          memory so that each (tile, bin) run is written with consecutive addresses.
 template <bool kScatter>
 __global__ void __launch_bounds__(kBucketThreads, 2)
-taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, int lut_w, int lut_h) {
+taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, int lut_w, int lut_h,
+                  const ChunkOrigin* __restrict__ origins) {
     extern __shared__ __align__(16) unsigned char bsm[];
     const int nh = kLocalBins * pl.n_tiles;
     const bool use_lut = ev.xmap != nullptr && ev.ymap != nullptr;
@@ -188,8 +222,6 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
     uint32_t* gbase = reinterpret_cast<uint32_t*>(bsm + lay.gbase);
     uint32_t* sorted = reinterpret_cast<uint32_t*>(bsm + lay.sorted);
     uint16_t* skey = reinterpret_cast<uint16_t*>(bsm + lay.skey);
-    __shared__ WinInfo s_win;
-    __shared__ int s_w0, s_gb0, s_single;
     __shared__ uint32_t s_tmp[kBucketThreads / 32 + 1];
 
     if (use_lut) {
@@ -201,30 +233,13 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
     for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const int64_t c0 = ev_first + (int64_t)chunk * (kBucketThreads * kBucketPerThread);
         const int64_t c1 = min(c0 + kBucketThreads * kBucketPerThread, ev_last);
+        const ChunkOrigin org = origins[chunk];            // same address for every thread: one broadcast load
         __syncthreads();                                   // previous chunk is done with smem
         for (int i = threadIdx.x; i < nh; i += kBucketThreads) hist[i] = 0;
-        if (threadIdx.x == 0) {
-            const int w0 = first_window(pl, c0);
-            int gb0 = 0, single = 0;
-            if (w0 < pl.n_windows) {
-                const WinInfo wi = load_window(pl, w0);
-                s_win = wi;
-                single = (c0 >= wi.begin && c1 <= wi.end && wi.nbins > 0) ? 1 : 0;
-                const int64_t i = c0 > wi.begin ? c0 : wi.begin;
-                gb0 = wi.binbase;
-                if (i < c1 && i < wi.end && wi.nbins > 0) {
-                    uint32_t z, d;
-                    bin_of(pl, wi, ev.t[i], z, d);
-                    gb0 += (int)z;
-                }
-            }
-            s_w0 = w0; s_gb0 = gb0; s_single = single;
-        }
-        __syncthreads();
-        const int gb0 = s_gb0;
-        const bool single = s_single != 0;
-        int w = s_w0;
-        WinInfo wi = s_win;
+        const int gb0 = org.gb0;
+        const bool single = org.single != 0;
+        int w = org.w0;
+        WinInfo wi = org.win;
 
         // all global loads of the chunk are issued before any of them is used
         uint32_t tt[kBucketPerThread];
@@ -236,9 +251,10 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
             if (i < c1) { tt[k] = __ldg(ev.t + i); xr[k] = __ldg(ev.x + i); yr[k] = __ldg(ev.y + i); pr[k] = __ldg(ev.p + i); }
         }
 
+        __syncthreads();                                   // histogram is zeroed
         // per event: (smem counter << 12) | rank inside the chunk, or kNone when dropped
         constexpr uint32_t kNone = 0xFFFFFFFFu;
-        uint32_t slot[kBucketPerThread], rec[kBucketPerThread];
+        uint32_t slot[kBucketPerThread], rec[kBucketPerThread] = {};
 
         // count / rank one classified event
         auto deposit = [&](int k, uint32_t tile, int gbin) {
@@ -275,7 +291,6 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
 #pragma unroll
             for (int k = 0; k < kBucketPerThread; ++k) {
                 slot[k] = kNone;
-                rec[k] = 0u;
                 uint32_t pix;
                 if (!locate(k, pix)) continue;
                 const uint32_t u = tt[k] >= start32 ? tt[k] - start32 : 0u;
@@ -605,49 +620,43 @@ taf_tile_kernel(TileParams tp) {
 #pragma unroll
                         for (int k = 0; k < K / 2; ++k) v[s][p][k] = __fadd2_rn(v[s][p][k], minus1);
             } else {
-                constexpr int G = SLOTS < 3 ? SLOTS : 3;            // accumulator loads in flight per group
+                // read and clear this thread's accumulators, then release `acc` for the next bin
+                // BEFORE the arithmetic: the long update phase runs without a barrier behind it
+                uint4 a[SLOTS];
 #pragma unroll
-                for (int g = 0; g < SLOTS; g += G) {
-                    uint4 a[G];
-#pragma unroll
-                    for (int i = 0; i < G; ++i) {
-                        const int s = g + i;
-                        a[i] = make_uint4(0u, 0u, 0u, 0u);
-                        if (s >= SLOTS) continue;
-                        const int lp = s * kTafThreads + tid;
-                        // every slot but the last lies inside the tile's accumulator array
-                        if (s < SLOTS - 1 || lp < pl.P) {
-                            a[i] = *reinterpret_cast<uint4*>(acc + 2 * lp);       // {n0, S0, n1, S1}
-                            if (a[i].x | a[i].z) *reinterpret_cast<uint4*>(acc + 2 * lp) = make_uint4(0u, 0u, 0u, 0u);
-                        }
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int lp = s * kTafThreads + tid;
+                    a[s] = make_uint4(0u, 0u, 0u, 0u);
+                    // every slot but the last lies inside the tile's accumulator array
+                    if (s < SLOTS - 1 || lp < pl.P) {
+                        a[s] = *reinterpret_cast<uint4*>(acc + 2 * lp);           // {n0, S0, n1, S1}
+                        if (a[s].x | a[s].z) *reinterpret_cast<uint4*>(acc + 2 * lp) = make_uint4(0u, 0u, 0u, 0u);
                     }
+                }
+                __syncthreads();
 #pragma unroll
-                    for (int i = 0; i < G; ++i) {
-                        const int s = g + i;
-                        if (s >= SLOTS) continue;
-                        const uint32_t nn[2] = {a[i].x, a[i].z}, ss[2] = {a[i].y, a[i].w};
+                for (int s = 0; s < SLOTS; ++s) {
+                    const uint32_t nn[2] = {a[s].x, a[s].z}, ss[2] = {a[s].y, a[s].w};
 #pragma unroll
-                        for (int p = 0; p < 2; ++p) {
-                            // mean(t_norm) - 1 = S / (n span) - 1 (generate_taf.py:23-27); for n == 0
-                            // the value is NaN and is never selected
-                            const bool active = nn[p] != 0u;
-                            float r;
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)nn[p] * tp.span));
-                            const float mean = fmaf((float)ss[p], r, -1.0f);
-                            float2 aged[K / 2];
+                    for (int p = 0; p < 2; ++p) {
+                        // mean(t_norm) - 1 = S / (n span) - 1 (generate_taf.py:23-27); for n == 0
+                        // the value is NaN and is never selected
+                        const bool active = nn[p] != 0u;
+                        float r;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)nn[p] * tp.span));
+                        const float mean = fmaf((float)ss[p], r, -1.0f);
+                        float2 aged[K / 2];
 #pragma unroll
-                            for (int k = 0; k < K / 2; ++k) aged[k] = __fadd2_rn(v[s][p][k], minus1);
+                        for (int k = 0; k < K / 2; ++k) aged[k] = __fadd2_rn(v[s][p][k], minus1);
 #pragma unroll
-                            for (int k = 0; k < K / 2; ++k) {
-                                const float next = (k + 1 < K / 2) ? aged[k + 1].x : mean;
-                                v[s][p][k].x = active ? aged[k].y : aged[k].x;
-                                v[s][p][k].y = active ? next : aged[k].y;
-                            }
+                        for (int k = 0; k < K / 2; ++k) {
+                            const float next = (k + 1 < K / 2) ? aged[k + 1].x : mean;
+                            v[s][p][k].x = active ? aged[k].y : aged[k].x;
+                            v[s][p][k].y = active ? next : aged[k].y;
                         }
                     }
                 }
             }
-            if (have) __syncthreads();                             // `acc` is clean again for the next bin
         }
         if (meta.flags & 2) {
             const bool write_state = tp.emit_state || (j == pl.n_batches - 1);
@@ -721,7 +730,7 @@ taf_tile_kernel(TileParams tp) {
 struct Layout {
     int P, n_tiles, slots;
     int64_t o_wbegin, o_wend, o_wstart, o_wnbins, o_wbinbase, o_batches, meta_bytes;
-    int64_t o_counts, o_binany, o_offrel, o_tiletotal, o_tilebase, o_records, total;
+    int64_t o_counts, o_binany, o_offrel, o_tiletotal, o_tilebase, o_origins, o_records, total;
     int n_batches_max;
 };
 
@@ -755,6 +764,7 @@ static int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W
     L.o_tiletotal = o; o += align_up(4ll * L.n_tiles, 16);
     L.o_tilebase = o; o += align_up(4ll * (L.n_tiles + 1), 16);
     o = align_up(o, 256);
+    L.o_origins = o;  o += align_up((int64_t)sizeof(ChunkOrigin) * (n_events / (kBucketThreads * kBucketPerThread) + 2), 256);
     L.o_records = o;  o += align_up(4ll * (n_events + 4ll * L.n_tiles), 256);
     L.total = o;
     return EVREP_OK;
@@ -902,8 +912,11 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
         EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
         EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
         SoA ev{t, x, y, p, xmap, ymap};
+        ChunkOrigin* origins = reinterpret_cast<ChunkOrigin*>(s + L.o_origins);
         if (grid > 0) {
-            taf_bucket_kernel<false><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h);
+            taf_chunk_origin_kernel<<<(int)((n_chunks + 255) / 256), 256, 0, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, origins);
+            EVREP_LAUNCH_CHECK();
+            taf_bucket_kernel<false><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins);
             EVREP_LAUNCH_CHECK();
         }
         taf_scan_rows_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
@@ -911,7 +924,7 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
         taf_scan_tiles_kernel<<<1, 1024, 0, st>>>(pl);
         EVREP_LAUNCH_CHECK();
         if (grid > 0) {
-            taf_bucket_kernel<true><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h);
+            taf_bucket_kernel<true><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins);
             EVREP_LAUNCH_CHECK();
         }
     } else {
