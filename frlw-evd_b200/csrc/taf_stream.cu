@@ -210,7 +210,7 @@ struct BucketSmem {
 template <bool kScatter>
 __global__ void __launch_bounds__(kBucketThreads, 2)
 taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, int lut_w, int lut_h,
-                  const ChunkOrigin* __restrict__ origins) {
+                  const ChunkOrigin* __restrict__ origins, int vec_ok) {
     extern __shared__ __align__(16) unsigned char bsm[];
     const int nh = kLocalBins * pl.n_tiles;
     const bool use_lut = ev.xmap != nullptr && ev.ymap != nullptr;
@@ -242,13 +242,37 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
         WinInfo wi = org.win;
 
         // all global loads of the chunk are issued before any of them is used
-        uint32_t tt[kBucketPerThread];
-        uint16_t xr[kBucketPerThread], yr[kBucketPerThread];
-        uint8_t pr[kBucketPerThread];
+        const bool fast = single && (c1 - c0) == kBucketThreads * kBucketPerThread &&
+                          wi.start >= 0 && wi.start <= 0xFFFFFFFFll;
+        // per event: timestamp and x | y << 14 | p << 28 (the .dat word), kBad when out of range
+        constexpr uint32_t kBad = 0xFFFFFFFFu;
+        auto pack = [](uint32_t x, uint32_t y, uint32_t p) -> uint32_t {
+            return (((x | y) >> 14) | (p >> 1)) ? kBad : (x | (y << 14) | (p << 28));
+        };
+        uint32_t tt[kBucketPerThread], xyp[kBucketPerThread];
+        if (fast && vec_ok) {
+            // 4 consecutive events per 128/64/64/32-bit load (c0 is a multiple of 4 events)
+            static_assert(kBucketPerThread % 4 == 0, "vector path loads events in groups of 4");
 #pragma unroll
-        for (int k = 0; k < kBucketPerThread; ++k) {
-            const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
-            if (i < c1) { tt[k] = __ldg(ev.t + i); xr[k] = __ldg(ev.x + i); yr[k] = __ldg(ev.y + i); pr[k] = __ldg(ev.p + i); }
+            for (int g = 0; g < kBucketPerThread / 4; ++g) {
+                const int64_t base = c0 + ((int64_t)g * kBucketThreads + threadIdx.x) * 4;
+                const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(ev.t + base));
+                const uint2 x4 = __ldg(reinterpret_cast<const uint2*>(ev.x + base));
+                const uint2 y4 = __ldg(reinterpret_cast<const uint2*>(ev.y + base));
+                const uint32_t p4 = __ldg(reinterpret_cast<const uint32_t*>(ev.p + base));
+                tt[4 * g + 0] = t4.x; tt[4 * g + 1] = t4.y; tt[4 * g + 2] = t4.z; tt[4 * g + 3] = t4.w;
+                xyp[4 * g + 0] = pack(x4.x & 0xFFFFu, y4.x & 0xFFFFu, p4 & 0xFFu);
+                xyp[4 * g + 1] = pack(x4.x >> 16, y4.x >> 16, (p4 >> 8) & 0xFFu);
+                xyp[4 * g + 2] = pack(x4.y & 0xFFFFu, y4.y & 0xFFFFu, (p4 >> 16) & 0xFFu);
+                xyp[4 * g + 3] = pack(x4.y >> 16, y4.y >> 16, p4 >> 24);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kBucketPerThread; ++k) {
+                const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
+                xyp[k] = kBad;
+                if (i < c1) { tt[k] = __ldg(ev.t + i); xyp[k] = pack(__ldg(ev.x + i), __ldg(ev.y + i), __ldg(ev.p + i)); }
+            }
         }
 
         __syncthreads();                                   // histogram is zeroed
@@ -272,8 +296,8 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
         };
         // map raw coordinates to the grid; false when the event is to be dropped
         auto locate = [&](int k, uint32_t& pix) -> bool {
-            uint32_t xm = xr[k], ym = yr[k];
-            bool ok = pr[k] < 2;
+            uint32_t xm = xyp[k] & 0x3FFFu, ym = (xyp[k] >> 14) & 0x3FFFu;
+            bool ok = xyp[k] != kBad;
             if (use_lut) {
                 ok = ok && xm < (uint32_t)lut_w && ym < (uint32_t)lut_h;
                 xm = s_lutx[min(xm, (uint32_t)lut_w - 1u)];
@@ -283,8 +307,6 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
             return ok && xm < W && ym < H;
         };
 
-        const bool fast = single && (c1 - c0) == kBucketThreads * kBucketPerThread &&
-                          wi.start >= 0 && wi.start <= 0xFFFFFFFFll;
         if (fast) {
             // the whole chunk lies in one window: 32-bit time arithmetic, no bounds checks
             const uint32_t start32 = (uint32_t)wi.start, zmax = (uint32_t)(wi.nbins - 1);
@@ -296,7 +318,7 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
                 const uint32_t u = tt[k] >= start32 ? tt[k] - start32 : 0u;
                 const uint32_t z = min(pl.div_abin.div(u), zmax);
                 const uint32_t tile = pl.div_P.div(pix);
-                if (kScatter) rec[k] = (min(u - z * pl.abin, kDMax) << 14) | ((pix - tile * pl.P) << 1) | pr[k];
+                if (kScatter) rec[k] = (min(u - z * pl.abin, kDMax) << 14) | ((pix - tile * pl.P) << 1) | (xyp[k] >> 28);
                 deposit(k, tile, wi.binbase + (int)z);
             }
         } else {
@@ -316,7 +338,7 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
                 uint32_t z, d;
                 bin_of(pl, wi, tt[k], z, d);
                 const uint32_t tile = pl.div_P.div(pix);
-                rec[k] = (d << 14) | ((pix - tile * pl.P) << 1) | pr[k];
+                rec[k] = (d << 14) | ((pix - tile * pl.P) << 1) | (xyp[k] >> 28);
                 deposit(k, tile, wi.binbase + (int)z);
             }
         }
@@ -900,7 +922,10 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
 
     if (TB > 0) {
         EVREP_CUDA(cudaMemsetAsync(s + L.o_counts, 0, (size_t)(L.o_offrel - L.o_counts), st));   // counts + bin_any
-        const int64_t ev_first = windows_host[0].ev_begin, ev_last = windows_host[n_windows - 1].ev_end;
+        // chunks start on a multiple of 4 events so that full chunks can use vector loads
+        const int64_t ev_first = windows_host[0].ev_begin & ~3ll, ev_last = windows_host[n_windows - 1].ev_end;
+        const int vec_ok = !((reinterpret_cast<uintptr_t>(t) & 15) | (reinterpret_cast<uintptr_t>(x) & 7) |
+                             (reinterpret_cast<uintptr_t>(y) & 7) | (reinterpret_cast<uintptr_t>(p) & 3));
         const int64_t per_cta = kBucketThreads * kBucketPerThread;
         const int64_t n_chunks = (ev_last - ev_first + per_cta - 1) / per_cta;
         if (n_chunks >= (1ll << 31)) return EVREP_ERR_RANGE;
@@ -916,7 +941,7 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
         if (grid > 0) {
             taf_chunk_origin_kernel<<<(int)((n_chunks + 255) / 256), 256, 0, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, origins);
             EVREP_LAUNCH_CHECK();
-            taf_bucket_kernel<false><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins);
+            taf_bucket_kernel<false><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins, vec_ok);
             EVREP_LAUNCH_CHECK();
         }
         taf_scan_rows_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
@@ -924,7 +949,7 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
         taf_scan_tiles_kernel<<<1, 1024, 0, st>>>(pl);
         EVREP_LAUNCH_CHECK();
         if (grid > 0) {
-            taf_bucket_kernel<true><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins);
+            taf_bucket_kernel<true><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins, vec_ok);
             EVREP_LAUNCH_CHECK();
         }
     } else {
