@@ -16,6 +16,7 @@
 //
 // HBM-bound byte/float work: no tensor cores.  Sums of d are exact integers, so the
 // result does not depend on the order in which records are accumulated.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -748,6 +749,332 @@ taf_tile_kernel(TileParams tp) {
     if (tp.bulk_out && tid < 2 * K) bulk_wait_all();               // smem must outlive the bulk reads
 }
 
+// ---- warp-specialised tile kernel -------------------------------------------------------------
+// Same algorithm as taf_tile_kernel, split into two roles so that the latency-bound record
+// bookkeeping runs ahead of, and concurrently with, the arithmetic:
+//   * producer warpgroup (warps 0-3, 56 registers after setmaxnreg.dec): walks the bins, waits for
+//     the TMA ring, accumulates (n, sum d) of bin b+1 into one of two accumulator buffers, refills
+//     the ring;
+//   * consumer warpgroups (warps 4-15, 152 registers after setmaxnreg.inc): own the FIFO state of
+//     the tile (6 pixels per thread), read + clear the accumulator of bin b, apply the update, and
+//     emit the window tensor through the staging tile + TMA bulk stores.
+// Hand-over uses named barriers (bar.arrive / bar.sync): FULL[buf] producer -> consumer,
+// EMPTY[buf] consumer -> producer.  4 warps per SM sub-partition: 1 producer + 3 consumers.
+constexpr int kProducerThreads = 128;
+constexpr int kConsumerThreads = 384;
+constexpr int kWsThreads = kProducerThreads + kConsumerThreads;
+constexpr int kWsMaxSlots = 6;
+constexpr int kWsChunkRecords = 512;    // 2 KB TMA bulk copies
+constexpr int kWsStages = 6;            // 12 KB ring
+
+enum : int { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarConsumers = 5, kBarProducers = 6 };
+
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct TileSmemWS {
+    int ring, acc, stage, bars, feed_p, feed_c, total;
+    static constexpr int kFeedBytes = 2 * (kBatchBins + 1) * 4 + 2 * kBatchBins * 4 + 2 * (int)sizeof(Batch) + 8;
+    __host__ __device__ TileSmemWS(int P, int K) {
+        int o = 0;
+        ring = o;   o += kWsStages * kWsChunkRecords * 4;
+        acc = o;    o += 2 * 2 * P * (int)sizeof(uint2);            // two buffers of {n, sum d} per (pixel, polarity)
+        stage = o;  o += 2 * K * P * 4;                             // [2K][P] output staging
+        bars = o;   o += 64;
+        feed_p = o; o += (kFeedBytes + 15) / 16 * 16;
+        feed_c = o; o += (kFeedBytes + 15) / 16 * 16;
+        total = o;
+    }
+};
+
+// Role-local view of the batch list: offsets / flags of the current batch in shared memory,
+// the next batch prefetched into registers (see taf_tile_kernel).
+struct BatchFeed {
+    uint32_t* s_off;       // [2][kBatchBins + 1]
+    uint32_t* s_any;       // [2][kBatchBins]
+    Batch* s_meta;         // [2]
+    const uint32_t* my_off;
+    const StreamPlan* pl;
+    int rtid, bar_id, nthreads;
+    Batch nmeta, nnmeta;
+    uint32_t pre_off, pre_any;
+
+    __device__ __forceinline__ void init(unsigned char* base, const StreamPlan* plan, const uint32_t* tile_off, int role_tid,
+                                         int barrier_id, int role_threads) {
+        s_off = reinterpret_cast<uint32_t*>(base);
+        s_any = s_off + 2 * (kBatchBins + 1);
+        s_meta = reinterpret_cast<Batch*>(s_any + 2 * kBatchBins);
+        my_off = tile_off; pl = plan; rtid = role_tid; bar_id = barrier_id; nthreads = role_threads;
+        const Batch m0 = pl->batches[0];
+        if (rtid == 0) s_meta[0] = m0;
+        if (rtid <= m0.nb) s_off[rtid] = my_off[m0.gbin0 + rtid];
+        if (rtid < m0.nb) s_any[rtid] = pl->bin_any[m0.gbin0 + rtid];
+        nmeta = pl->batches[pl->n_batches > 1 ? 1 : 0];
+        named_sync(bar_id, nthreads);
+    }
+    __device__ __forceinline__ Batch begin(int j) {          // start of batch j: issue the prefetches
+        pre_off = 0; pre_any = 0; nnmeta = nmeta;
+        if (j + 1 < pl->n_batches) {
+            if (rtid <= nmeta.nb) pre_off = my_off[nmeta.gbin0 + rtid];
+            if (rtid < nmeta.nb) pre_any = pl->bin_any[nmeta.gbin0 + rtid];
+            if (j + 2 < pl->n_batches) nnmeta = pl->batches[j + 2];
+        }
+        return s_meta[j & 1];
+    }
+    __device__ __forceinline__ void end(int j) {             // end of batch j: publish batch j+1
+        if (j + 1 < pl->n_batches) {
+            const int nb = (j & 1) ^ 1;
+            if (rtid == 0) s_meta[nb] = nmeta;
+            if (rtid <= nmeta.nb) s_off[nb * (kBatchBins + 1) + rtid] = pre_off;
+            if (rtid < nmeta.nb) s_any[nb * kBatchBins + rtid] = pre_any;
+            nmeta = nnmeta;
+        }
+        named_sync(bar_id, nthreads);
+    }
+};
+
+template <int K, int SLOTS>
+__global__ void __launch_bounds__(kWsThreads, 1)
+taf_tile_ws_kernel(TileParams tp) {
+    const StreamPlan& pl = tp.pl;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TileSmemWS lay(pl.P, K);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + lay.ring);     // [kWsStages][kWsChunkRecords]
+    uint2* acc = reinterpret_cast<uint2*>(smem_raw + lay.acc);             // [2][2P]
+    float* stage = reinterpret_cast<float*>(smem_raw + lay.stage);         // [2K][P]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);
+
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int64_t HW = (int64_t)pl.H * pl.W;
+    const int64_t pix0 = (int64_t)tile * pl.P;
+    const int npix = (int)min((int64_t)pl.P, HW - pix0);
+    const uint32_t* my_off = pl.off_rel + (int64_t)tile * (pl.TB + 1);
+
+    if (tid == 0) {
+        for (int s = 0; s < kWsStages; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 4 * pl.P; i += kWsThreads) acc[i] = make_uint2(0u, 0u);
+    __syncthreads();
+
+    if (tid < kProducerThreads) {
+        // ================================ producer warpgroup ================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const uint32_t* my_records = pl.records + pl.tile_base[tile];
+        const uint32_t list_len = (pl.tile_total[tile] + 3u) & ~3u;
+        const int n_chunks = (int)((list_len + kWsChunkRecords - 1) / kWsChunkRecords);
+        auto issue = [&](int c) {           // producer thread 0 only
+            const uint32_t first = (uint32_t)c * kWsChunkRecords;
+            const uint32_t bytes = min((uint32_t)kWsChunkRecords, list_len - first) * 4u;
+            uint64_t* bar = full + (c % kWsStages);
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(ring + (c % kWsStages) * kWsChunkRecords, my_records + first, bytes, bar);
+        };
+        if (tid == 0)
+            for (int c = 0; c < n_chunks && c < kWsStages; ++c) issue(c);
+        BatchFeed feed;
+        feed.init(smem_raw + lay.feed_p, &pl, my_off, tid, kBarProducers, kProducerThreads);
+        int ready_chunk = -1, next_refill = kWsStages, buf = 0;
+        int uses0 = 0, uses1 = 0;
+        for (int j = 0; j < pl.n_batches; ++j) {
+            const Batch meta = feed.begin(j);
+            const int jb = j & 1;
+            for (int b = 0; b < meta.nb; ++b) {
+                const uint32_t o0 = feed.s_off[jb * (kBatchBins + 1) + b], o1 = feed.s_off[jb * (kBatchBins + 1) + b + 1];
+                if (!feed.s_any[jb * kBatchBins + b] || o1 <= o0) continue;
+                // the consumers must have drained this buffer (its first use needs no wait)
+                if ((buf ? uses1 : uses0) > 0) named_sync(kBarEmpty0 + buf, kWsThreads);
+                uint2* my_acc = acc + buf * 2 * pl.P;
+                uint32_t cur = o0;
+                while (cur < o1) {
+                    const int c = (int)(cur / kWsChunkRecords);
+                    const uint32_t chunk_end = (uint32_t)(c + 1) * kWsChunkRecords;
+                    const uint32_t seg_end = o1 < chunk_end ? o1 : chunk_end;
+                    if (c >= next_refill) {          // a single bin longer than the ring: recycle drained stages now
+                        named_sync(kBarProducers, kProducerThreads);
+                        if (tid == 0)
+                            for (int r = next_refill; r <= c && r < n_chunks; ++r) issue(r);
+                        next_refill = c + 1;
+                    }
+                    if (c > ready_chunk) { mbar_wait(full + (c % kWsStages), (uint32_t)(c / kWsStages) & 1u); ready_chunk = c; }
+                    const uint32_t* chunk = ring + (c % kWsStages) * kWsChunkRecords;
+                    for (uint32_t r = cur + tid; r < seg_end; r += kProducerThreads) {
+                        const uint32_t rec = chunk[r & (kWsChunkRecords - 1)];
+                        uint2* cell = my_acc + (rec & 0x3FFFu);      // 2 * local pixel + p
+                        atomicAdd(&cell->x, 1u);
+                        atomicAdd(&cell->y, rec >> 14);
+                    }
+                    cur = seg_end;
+                }
+                named_arrive(kBarFull0 + buf, kWsThreads);           // hand the accumulator to the consumers
+                if (buf) ++uses1; else ++uses0;
+                buf ^= 1;
+                // ring stages whose chunk ends at or before o1 are drained by every producer thread
+                const int drained = (int)(o1 / kWsChunkRecords);
+                if (drained + kWsStages > next_refill) {
+                    named_sync(kBarProducers, kProducerThreads);
+                    if (tid == 0)
+                        for (int r = next_refill; r < drained + kWsStages && r < n_chunks; ++r) issue(r);
+                    next_refill = drained + kWsStages;
+                }
+            }
+            feed.end(j);
+        }
+        // match the consumers' last EMPTY arrivals so that no barrier phase is left open
+        if (uses0 > 0) named_sync(kBarEmpty0, kWsThreads);
+        if (uses1 > 0) named_sync(kBarEmpty1, kWsThreads);
+        return;
+    }
+
+    // =================================== consumer warpgroups ===================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int ctid = tid - kProducerThreads;
+    static_assert(K % 4 == 0, "K must be a multiple of 4");
+    float2 v[SLOTS][2][K / 2];
+    const bool first_fresh = (pl.batches[0].flags & 1) != 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int lp = s * kConsumerThreads + ctid;
+        if (lp < npix && !first_fresh) {
+            const float4* src = reinterpret_cast<const float4*>(tp.state + (pix0 + lp) * 2 * K);
+#pragma unroll
+            for (int q = 0; q < 2 * K / 4; ++q) {
+                const float4 f = src[q];
+                v[s][(q * 4) / K][((q * 4) % K) / 2 + 0] = make_float2(f.x, f.y);
+                v[s][(q * 4) / K][((q * 4) % K) / 2 + 1] = make_float2(f.z, f.w);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int k = 0; k < K / 2; ++k) v[s][p][k] = make_float2(kTafInit, kTafInit);
+        }
+    }
+    BatchFeed feed;
+    feed.init(smem_raw + lay.feed_c, &pl, my_off, ctid, kBarConsumers, kConsumerThreads);
+    int buf = 0;
+    bool staged_once = false;
+    const float2 minus1 = make_float2(-1.0f, -1.0f);
+    for (int j = 0; j < pl.n_batches; ++j) {
+        const Batch meta = feed.begin(j);
+        const int jb = j & 1;
+        if (meta.flags & 1) {
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int k = 0; k < K / 2; ++k) v[s][p][k] = make_float2(kTafInit, kTafInit);
+        }
+        for (int b = 0; b < meta.nb; ++b) {
+            const uint32_t o0 = feed.s_off[jb * (kBatchBins + 1) + b], o1 = feed.s_off[jb * (kBatchBins + 1) + b + 1];
+            if (!feed.s_any[jb * kBatchBins + b]) continue;          // nobody saw an event: no ageing
+            if (o1 <= o0) {
+                // the tile saw nothing in this bin, but some other tile did: everything ages
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+                    for (int p = 0; p < 2; ++p)
+#pragma unroll
+                        for (int k = 0; k < K / 2; ++k) v[s][p][k] = __fadd2_rn(v[s][p][k], minus1);
+                continue;
+            }
+            named_sync(kBarFull0 + buf, kWsThreads);                 // the producers filled this accumulator
+            uint2* my_acc = acc + buf * 2 * pl.P;
+            uint4 a[SLOTS];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int lp = s * kConsumerThreads + ctid;
+                a[s] = make_uint4(0u, 0u, 0u, 0u);
+                if (s < SLOTS - 1 || lp < pl.P) {                    // every slot but the last lies inside the array
+                    a[s] = *reinterpret_cast<uint4*>(my_acc + 2 * lp);               // {n0, S0, n1, S1}
+                    if (a[s].x | a[s].z) *reinterpret_cast<uint4*>(my_acc + 2 * lp) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            named_arrive(kBarEmpty0 + buf, kWsThreads);              // clean again: give it back
+            buf ^= 1;
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const uint32_t nn[2] = {a[s].x, a[s].z}, ss[2] = {a[s].y, a[s].w};
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    // mean(t_norm) - 1 = S / (n span) - 1 (generate_taf.py:23-27); NaN for n == 0, never selected
+                    const bool active = nn[p] != 0u;
+                    float r;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)nn[p] * tp.span));
+                    const float mean = fmaf((float)ss[p], r, -1.0f);
+                    float2 aged[K / 2];
+#pragma unroll
+                    for (int k = 0; k < K / 2; ++k) aged[k] = __fadd2_rn(v[s][p][k], minus1);
+#pragma unroll
+                    for (int k = 0; k < K / 2; ++k) {
+                        const float next = (k + 1 < K / 2) ? aged[k + 1].x : mean;
+                        v[s][p][k].x = active ? aged[k].y : aged[k].x;
+                        v[s][p][k].y = active ? next : aged[k].y;
+                    }
+                }
+            }
+        }
+        if (meta.flags & 2) {
+            const bool write_state = tp.emit_state || (j == pl.n_batches - 1);
+            float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
+            if (tp.bulk_out) {
+                if (staged_once) {
+                    if (ctid < 2 * K) bulk_wait_read();              // previous window's rows have left smem
+                    named_sync(kBarConsumers, kConsumerThreads);
+                }
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int lp = s * kConsumerThreads + ctid;
+                    if (s == SLOTS - 1 && lp >= pl.P) continue;     // columns >= npix are staged but never stored
+#pragma unroll
+                    for (int k = 0; k < K / 2; ++k)
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            stage[(4 * k + p) * pl.P + lp] = v[s][p][k].x;
+                            stage[(4 * k + 2 + p) * pl.P + lp] = v[s][p][k].y;
+                        }
+                }
+                fence_async_smem();
+                named_sync(kBarConsumers, kConsumerThreads);
+                if (ctid < 2 * K) {
+                    bulk_store_1d(o + (int64_t)ctid * HW, stage + ctid * pl.P, (uint32_t)npix * 4u);
+                    bulk_commit();
+                }
+                staged_once = true;
+            } else {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int lp = s * kConsumerThreads + ctid;
+                    if (lp >= npix) continue;
+#pragma unroll
+                    for (int k = 0; k < K / 2; ++k)
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            __stcs(o + (int64_t)(4 * k + p) * HW + lp, v[s][p][k].x);
+                            __stcs(o + (int64_t)(4 * k + 2 + p) * HW + lp, v[s][p][k].y);
+                        }
+                }
+            }
+            if (write_state) {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int lp = s * kConsumerThreads + ctid;
+                    if (lp >= npix) continue;
+                    float4* dst = reinterpret_cast<float4*>(tp.state + (pix0 + lp) * 2 * K);
+#pragma unroll
+                    for (int q = 0; q < 2 * K / 4; ++q) {
+                        const float2 lo = v[s][(q * 4) / K][((q * 4) % K) / 2], hi = v[s][(q * 4) / K][((q * 4) % K) / 2 + 1];
+                        dst[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    }
+                }
+            }
+        }
+        feed.end(j);
+    }
+    if (tp.bulk_out && ctid < 2 * K) bulk_wait_all();               // smem must outlive the bulk reads
+}
+
 // ---- host side -------------------------------------------------------------------------
 struct Layout {
     int P, n_tiles, slots;
@@ -794,6 +1121,24 @@ static int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W
 
 static inline int64_t batches_upper_bound(int n_windows, int64_t TB) {
     return (int64_t)n_windows + TB / kBatchBins + 1;
+}
+
+template <int K>
+static int launch_tiles_ws(const TileParams& tp, cudaStream_t st) {
+    const int slots = (tp.pl.P + kConsumerThreads - 1) / kConsumerThreads;
+    const size_t smem = (size_t)TileSmemWS(tp.pl.P, K).total;
+#define EVREP_TILE_WS(S)                                                                                  \
+    case S:                                                                                               \
+        EVREP_CUDA(cudaFuncSetAttribute(taf_tile_ws_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        taf_tile_ws_kernel<K, S><<<tp.pl.n_tiles, kWsThreads, smem, st>>>(tp);                            \
+        break;
+    switch (slots) {
+        EVREP_TILE_WS(1) EVREP_TILE_WS(2) EVREP_TILE_WS(3) EVREP_TILE_WS(4) EVREP_TILE_WS(5) EVREP_TILE_WS(6)
+        default: return EVREP_ERR_RANGE;
+    }
+#undef EVREP_TILE_WS
+    EVREP_LAUNCH_CHECK();
+    return EVREP_OK;
 }
 
 template <int K>
@@ -958,7 +1303,10 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
 
     const size_t smem = (size_t)TileSmem(L.P, K).total;
     if (ev_tiles_begin) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_begin), st));
-    rc = K == 8 ? launch_tiles<8>(tp, L.slots, smem, st) : launch_tiles<4>(tp, L.slots, smem, st);
+    const char* legacy = getenv("EVREP_TAF_TILE_KERNEL");            // "single" = the non-specialised kernel (A/B runs)
+    const bool ws = !(legacy && strcmp(legacy, "single") == 0) && (size_t)TileSmemWS(L.P, K).total <= 232448;
+    if (ws) rc = K == 8 ? launch_tiles_ws<8>(tp, st) : launch_tiles_ws<4>(tp, st);
+    else rc = K == 8 ? launch_tiles<8>(tp, L.slots, smem, st) : launch_tiles<4>(tp, L.slots, smem, st);
     if (rc) return rc;
     if (ev_tiles_end) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_end), st));
     return EVREP_OK;
