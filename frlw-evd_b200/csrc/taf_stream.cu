@@ -29,7 +29,7 @@ constexpr int kTafThreads = 384;        // threads per tile CTA: 3 warps per SM 
 constexpr int kMaxSlots = 6;            // pixels per thread held in registers (6 x 384 = 2304 >= 2240)
 constexpr int kChunkRecords = 1024;     // records per TMA bulk copy (4 KB)
 constexpr int kStages = 8;              // ring depth (32 KB in flight per SM)
-constexpr int kBatchBins = 32;          // bins whose offsets are staged in smem at once
+constexpr int kBatchBins = 16;          // bins whose offsets are staged in smem at once
 constexpr int kMaxTiles = 2048;         // kLocalBins * kMaxTiles counters fit the 13-bit key of the scatter pass
 constexpr int kLocalBins = 4;           // bins covered by a bucketing CTA's smem histogram
 constexpr int kBucketThreads = 512;
@@ -763,9 +763,10 @@ taf_tile_kernel(TileParams tp) {
 constexpr int kProducerThreads = 128;
 constexpr int kConsumerThreads = 384;
 constexpr int kWsThreads = kProducerThreads + kConsumerThreads;
-constexpr int kWsMaxSlots = 6;
 constexpr int kWsChunkRecords = 512;    // 2 KB TMA bulk copies
-constexpr int kWsStages = 6;            // 12 KB ring
+constexpr int kWsStages = 8;            // 16 KB ring = a flat circular buffer of 4096 records
+constexpr int kWsRing = kWsChunkRecords * kWsStages;
+static_assert((kWsRing & (kWsRing - 1)) == 0, "ring size must be a power of two");
 
 enum : int { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarConsumers = 5, kBarProducers = 6 };
 
@@ -821,7 +822,7 @@ struct BatchFeed {
         }
         return s_meta[j & 1];
     }
-    __device__ __forceinline__ void end(int j) {             // end of batch j: publish batch j+1
+    __device__ __forceinline__ void publish(int j) {         // store batch j+1; the caller supplies the barrier
         if (j + 1 < pl->n_batches) {
             const int nb = (j & 1) ^ 1;
             if (rtid == 0) s_meta[nb] = nmeta;
@@ -829,6 +830,9 @@ struct BatchFeed {
             if (rtid < nmeta.nb) s_any[nb * kBatchBins + rtid] = pre_any;
             nmeta = nnmeta;
         }
+    }
+    __device__ __forceinline__ void end(int j) {             // end of batch j: publish batch j+1
+        publish(j);
         named_sync(bar_id, nthreads);
     }
 };
@@ -882,29 +886,49 @@ taf_tile_ws_kernel(TileParams tp) {
             for (int b = 0; b < meta.nb; ++b) {
                 const uint32_t o0 = feed.s_off[jb * (kBatchBins + 1) + b], o1 = feed.s_off[jb * (kBatchBins + 1) + b + 1];
                 if (!feed.s_any[jb * kBatchBins + b] || o1 <= o0) continue;
-                // the consumers must have drained this buffer (its first use needs no wait)
-                if ((buf ? uses1 : uses0) > 0) named_sync(kBarEmpty0 + buf, kWsThreads);
                 uint2* my_acc = acc + buf * 2 * pl.P;
-                uint32_t cur = o0;
-                while (cur < o1) {
-                    const int c = (int)(cur / kWsChunkRecords);
-                    const uint32_t chunk_end = (uint32_t)(c + 1) * kWsChunkRecords;
-                    const uint32_t seg_end = o1 < chunk_end ? o1 : chunk_end;
-                    if (c >= next_refill) {          // a single bin longer than the ring: recycle drained stages now
-                        named_sync(kBarProducers, kProducerThreads);
-                        if (tid == 0)
-                            for (int r = next_refill; r <= c && r < n_chunks; ++r) issue(r);
-                        next_refill = c + 1;
+                const int last_c = (int)((o1 - 1) / kWsChunkRecords);
+                if (last_c < next_refill) {
+                    // common case: every chunk of the bin is already in flight
+                    while (ready_chunk < last_c) {
+                        ++ready_chunk;
+                        mbar_wait(full + (ready_chunk % kWsStages), (uint32_t)(ready_chunk / kWsStages) & 1u);
                     }
-                    if (c > ready_chunk) { mbar_wait(full + (c % kWsStages), (uint32_t)(c / kWsStages) & 1u); ready_chunk = c; }
-                    const uint32_t* chunk = ring + (c % kWsStages) * kWsChunkRecords;
-                    for (uint32_t r = cur + tid; r < seg_end; r += kProducerThreads) {
-                        const uint32_t rec = chunk[r & (kWsChunkRecords - 1)];
+                    // the consumers must have drained this buffer (its first use needs no wait)
+                    if ((buf ? uses1 : uses0) > 0) named_sync(kBarEmpty0 + buf, kWsThreads);
+#pragma unroll 4
+                    for (uint32_t r = o0 + tid; r < o1; r += kProducerThreads) {
+                        const uint32_t rec = ring[r & (kWsRing - 1)];
                         uint2* cell = my_acc + (rec & 0x3FFFu);      // 2 * local pixel + p
                         atomicAdd(&cell->x, 1u);
                         atomicAdd(&cell->y, rec >> 14);
                     }
-                    cur = seg_end;
+                } else {
+                    // a single bin longer than the ring: go chunk by chunk, recycling drained stages
+                    if ((buf ? uses1 : uses0) > 0) named_sync(kBarEmpty0 + buf, kWsThreads);
+                    uint32_t cur = o0;
+                    while (cur < o1) {
+                        const int c = (int)(cur / kWsChunkRecords);
+                        const uint32_t chunk_end = (uint32_t)(c + 1) * kWsChunkRecords;
+                        const uint32_t seg_end = o1 < chunk_end ? o1 : chunk_end;
+                        if (c >= next_refill) {
+                            named_sync(kBarProducers, kProducerThreads);
+                            if (tid == 0)
+                                for (int r = next_refill; r <= c && r < n_chunks; ++r) issue(r);
+                            next_refill = c + 1;
+                        }
+                        while (ready_chunk < c) {
+                            ++ready_chunk;
+                            mbar_wait(full + (ready_chunk % kWsStages), (uint32_t)(ready_chunk / kWsStages) & 1u);
+                        }
+                        for (uint32_t r = cur + tid; r < seg_end; r += kProducerThreads) {
+                            const uint32_t rec = ring[r & (kWsRing - 1)];
+                            uint2* cell = my_acc + (rec & 0x3FFFu);
+                            atomicAdd(&cell->x, 1u);
+                            atomicAdd(&cell->y, rec >> 14);
+                        }
+                        cur = seg_end;
+                    }
                 }
                 named_arrive(kBarFull0 + buf, kWsThreads);           // hand the accumulator to the consumers
                 if (buf) ++uses1; else ++uses0;
@@ -1015,6 +1039,7 @@ taf_tile_ws_kernel(TileParams tp) {
                 }
             }
         }
+        bool published = false;
         if (meta.flags & 2) {
             const bool write_state = tp.emit_state || (j == pl.n_batches - 1);
             float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
@@ -1036,7 +1061,9 @@ taf_tile_ws_kernel(TileParams tp) {
                         }
                 }
                 fence_async_smem();
+                feed.publish(j);                                     // next batch's offsets ride on the same barrier
                 named_sync(kBarConsumers, kConsumerThreads);
+                published = true;
                 if (ctid < 2 * K) {
                     bulk_store_1d(o + (int64_t)ctid * HW, stage + ctid * pl.P, (uint32_t)npix * 4u);
                     bulk_commit();
@@ -1070,7 +1097,7 @@ taf_tile_ws_kernel(TileParams tp) {
                 }
             }
         }
-        feed.end(j);
+        if (!published) feed.end(j);
     }
     if (tp.bulk_out && ctid < 2 * K) bulk_wait_all();               // smem must outlive the bulk reads
 }
