@@ -888,24 +888,51 @@ taf_tile_ws_kernel(TileParams tp) {
                 if (!feed.s_any[jb * kBatchBins + b] || o1 <= o0) continue;
                 uint2* my_acc = acc + buf * 2 * pl.P;
                 const int last_c = (int)((o1 - 1) / kWsChunkRecords);
+                const bool had_use = (buf ? uses1 : uses0) > 0;
                 if (last_c < next_refill) {
                     // common case: every chunk of the bin is already in flight
                     while (ready_chunk < last_c) {
                         ++ready_chunk;
                         mbar_wait(full + (ready_chunk % kWsStages), (uint32_t)(ready_chunk / kWsStages) & 1u);
                     }
-                    // the consumers must have drained this buffer (its first use needs no wait)
-                    if ((buf ? uses1 : uses0) > 0) named_sync(kBarEmpty0 + buf, kWsThreads);
-#pragma unroll 4
-                    for (uint32_t r = o0 + tid; r < o1; r += kProducerThreads) {
+                    // records are pulled into registers BEFORE waiting for the accumulator buffer
+                    constexpr int kPre = 8;
+                    constexpr uint32_t kNoRec = 0xFFFFFFFFu;        // d = 2^18-1, pixel 8191: never produced for P <= 2560
+                    uint32_t pre[kPre];
+#pragma unroll
+                    for (int i = 0; i < kPre; ++i) {
+                        const uint32_t r = o0 + tid + i * kProducerThreads;
+                        pre[i] = r < o1 ? ring[r & (kWsRing - 1)] : kNoRec;
+                    }
+                    const bool all_pre = (o1 - o0) <= (uint32_t)(kPre * kProducerThreads);
+                    // the consumers must have drained this buffer (its first use needs no wait); the
+                    // barrier also tells that every producer thread is done with all earlier bins
+                    if (had_use) named_sync(kBarEmpty0 + buf, kWsThreads);
+                    else named_sync(kBarProducers, kProducerThreads);
+                    {
+                        // ring stages whose chunk ends before the first record still to be read are free
+                        const int drained = (int)((all_pre ? o1 : o0) / kWsChunkRecords);
+                        if (tid == 0)
+                            for (int r = next_refill; r < drained + kWsStages && r < n_chunks; ++r) issue(r);
+                        if (drained + kWsStages > next_refill) next_refill = drained + kWsStages;
+                    }
+#pragma unroll
+                    for (int i = 0; i < kPre; ++i) {
+                        if (pre[i] != kNoRec) {
+                            uint2* cell = my_acc + (pre[i] & 0x3FFFu);   // 2 * local pixel + p
+                            atomicAdd(&cell->x, 1u);
+                            atomicAdd(&cell->y, pre[i] >> 14);
+                        }
+                    }
+                    for (uint32_t r = o0 + tid + kPre * kProducerThreads; r < o1; r += kProducerThreads) {
                         const uint32_t rec = ring[r & (kWsRing - 1)];
-                        uint2* cell = my_acc + (rec & 0x3FFFu);      // 2 * local pixel + p
+                        uint2* cell = my_acc + (rec & 0x3FFFu);
                         atomicAdd(&cell->x, 1u);
                         atomicAdd(&cell->y, rec >> 14);
                     }
                 } else {
                     // a single bin longer than the ring: go chunk by chunk, recycling drained stages
-                    if ((buf ? uses1 : uses0) > 0) named_sync(kBarEmpty0 + buf, kWsThreads);
+                    if (had_use) named_sync(kBarEmpty0 + buf, kWsThreads);
                     uint32_t cur = o0;
                     while (cur < o1) {
                         const int c = (int)(cur / kWsChunkRecords);
@@ -933,14 +960,6 @@ taf_tile_ws_kernel(TileParams tp) {
                 named_arrive(kBarFull0 + buf, kWsThreads);           // hand the accumulator to the consumers
                 if (buf) ++uses1; else ++uses0;
                 buf ^= 1;
-                // ring stages whose chunk ends at or before o1 are drained by every producer thread
-                const int drained = (int)(o1 / kWsChunkRecords);
-                if (drained + kWsStages > next_refill) {
-                    named_sync(kBarProducers, kProducerThreads);
-                    if (tid == 0)
-                        for (int r = next_refill; r < drained + kWsStages && r < n_chunks; ++r) issue(r);
-                    next_refill = drained + kWsStages;
-                }
             }
             feed.end(j);
         }
