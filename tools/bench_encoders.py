@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the headline): per-window encoders and the decoder on the
+1MP synthetic stream, CUDA-event timed, with the SURVEY 8d algorithmic bytes and the
+fraction of the measured HBM peak.  One JSON line per encoder.
+
+  python tools/bench_encoders.py [--seconds 2] [--iters 5]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from frlw_evd_b200 import ops, synth  # noqa: E402
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=2.0)
+    ap.add_argument("--iters", type=int, default=5)
+    args = ap.parse_args()
+    peak, _ = bench.load_peaks()
+    dev = torch.device("cuda", 0)
+    t, x, y, p = bench.get_stream(1002, args.seconds, 1e7)
+    n = len(t)
+    ev = ops.EventStream.from_numpy(t, x, y, p, dev)
+    maps = ops.make_coord_maps(bench.SENSOR, bench.GRID, dev)
+    H, W = bench.GRID
+    HW = H * W
+    edges = np.searchsorted(t, np.arange(0, int(args.seconds * 1e6) + 1, 50000))
+    windows = [(int(edges[i]), int(edges[i + 1]), i * 50000) for i in range(len(edges) - 1)]
+    nw = len(windows)
+
+    def report(name, ms, algo_bytes, events, extra=None):
+        line = {"encoder": name, "ms": ms, "Mevents_per_s": events / ms / 1e3, "algorithmic_bytes": algo_bytes,
+                "achieved_GBs": algo_bytes / ms / 1e6, "frac_of_measured_peak": algo_bytes / ms / 1e6 / peak,
+                "events": events, "windows": nw}
+        line.update(extra or {})
+        print(json.dumps(line))
+
+    # decode: 8 B in, 9 B out per event
+    raw = torch.from_numpy(synth.pack_dat_records(t, x, y, p).view(np.uint8)).to(dev)
+    dec = ops.EventStream.empty(n, dev)
+    report("decode_dat", timed(lambda: ops.decode_dat(raw, dec), args.iters), 17 * n, n)
+
+    for K in (5, 8):
+        out = torch.empty((2 * K, H, W), dtype=torch.float32, device=dev)
+
+        def run_ev():
+            for lo, hi, t0 in windows:
+                ops.event_volume(ev.slice(lo, hi), t0, 50000, (H, W), K, maps, out)
+        report("event_volume_K%d_50ms_windows" % K, timed(run_ev, args.iters), 9 * n + nw * 8 * K * HW, n)
+
+    def run_eci():
+        for lo, hi, _ in windows:
+            ops.count_image(ev.slice(lo, hi), (H, W), maps)
+    report("count_image_50ms_windows", timed(run_eci, args.iters), 5 * n + nw * 8 * HW, n)
+
+    lam = [0.00001, 0.0000025, 0.000001]
+
+    def run_sae():
+        mem = None
+        for lo, hi, t0 in windows:
+            _, mem = ops.sae(ev.slice(lo, hi), (H, W), lam, mem, t0 + 50000, maps)
+    report("sae_3lambda_50ms_windows", timed(run_sae, args.iters), 9 * n + nw * (8 * 3 * HW + 8 * HW), n)
+
+
+if __name__ == "__main__":
+    main()
