@@ -22,6 +22,11 @@ class TafWindow(ctypes.Structure):
                 ("n_bins", c_int32), ("fresh", c_int32)]
 
 
+class EvWindow(ctypes.Structure):
+    """``evrep_ev_window`` (include/evrep.h)."""
+    _fields_ = [("ev_begin", c_int64), ("ev_end", c_int64), ("t0", c_int64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/evrep.h declares
 SIGNATURES = {
     "evrep_version": (c_int, []),
@@ -44,6 +49,9 @@ SIGNATURES = {
     "evrep_taf_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int64, c_int, c_int]),
     "evrep_taf_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int,
                                  P, c_int64, P, c_int64, P, P, P]),
+    "evrep_event_volume_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "evrep_event_volume_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int64, c_int, c_int, c_int, P, P, c_int, c_int,
+                                          P, c_int64, P, c_int64, P]),
     "evrep_nearest_resize": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "evrep_quantize_u8": (c_int, [P, c_int64, c_int, P, P]),
     "evrep_taf_leaky_u8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),

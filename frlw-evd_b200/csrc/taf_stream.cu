@@ -1121,6 +1121,158 @@ taf_tile_ws_kernel(TileParams tp) {
     if (tp.bulk_out && ctid < 2 * K) bulk_wait_all();               // smem must outlive the bulk reads
 }
 
+// ---- Event Volume over whole streams ----------------------------------------------------------
+// generate_eventvolume.py:15-42 for a list of non-overlapping windows: the same bucketing (one
+// "bin" per window, d = t - t0) feeds one CTA per sensor tile.  The tile's [2K][P] float
+// accumulator lives in shared memory and doubles as the staging area of the TMA bulk stores:
+// zero -> splat (shared-memory float atomics) -> scale by /5*255 in place -> one bulk store per
+// channel row.  Records arrive through the same ring of TMA bulk copies as in the TAF kernel.
+constexpr int kEvThreads = 512;
+
+struct EvTileParams {
+    StreamPlan pl;
+    float* out;
+    int64_t out_stride;
+    double tw;             // window length: t_norm = d / tw in float64 (generate_eventvolume.py:141)
+    int K;
+    int bulk_out;
+};
+
+struct EvTileSmem {
+    int ring, acc, bars, feed, total;
+    __host__ __device__ EvTileSmem(int P, int K) {
+        int o = 0;
+        ring = o; o += kWsRing * 4;
+        acc = o;  o += 2 * K * P * 4;
+        bars = o; o += 64;
+        feed = o; o += (TileSmemWS::kFeedBytes + 15) / 16 * 16;
+        total = o;
+    }
+};
+
+__global__ void __launch_bounds__(kEvThreads, 1)
+ev_tile_kernel(EvTileParams tp) {
+    const StreamPlan& pl = tp.pl;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const EvTileSmem lay(pl.P, tp.K);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + lay.ring);
+    float* acc = reinterpret_cast<float*>(smem_raw + lay.acc);             // [2K][P]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);
+
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int K = tp.K, rows = 2 * K;
+    const int64_t HW = (int64_t)pl.H * pl.W;
+    const int64_t pix0 = (int64_t)tile * pl.P;
+    const int npix = (int)min((int64_t)pl.P, HW - pix0);
+    const uint32_t* my_off = pl.off_rel + (int64_t)tile * (pl.TB + 1);
+    const uint32_t* my_records = pl.records + pl.tile_base[tile];
+    const uint32_t list_len = (pl.tile_total[tile] + 3u) & ~3u;
+    const int n_chunks = (int)((list_len + kWsChunkRecords - 1) / kWsChunkRecords);
+    auto issue = [&](int c) {           // thread 0 only
+        const uint32_t first = (uint32_t)c * kWsChunkRecords;
+        const uint32_t bytes = min((uint32_t)kWsChunkRecords, list_len - first) * 4u;
+        uint64_t* bar = full + (c % kWsStages);
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(ring + (c % kWsStages) * kWsChunkRecords, my_records + first, bytes, bar);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kWsStages; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int c = 0; c < n_chunks && c < kWsStages; ++c) issue(c);
+    BatchFeed feed;
+    feed.init(smem_raw + lay.feed, &pl, my_off, tid, 0, kEvThreads);       // barrier 0 = the whole CTA
+
+    int ready_chunk = -1, next_refill = kWsStages;
+    bool staged_once = false;
+    const float Kf = (float)K;
+    const int n4 = rows * pl.P / 4;
+    for (int j = 0; j < pl.n_batches; ++j) {
+        const Batch meta = feed.begin(j);
+        const int jb = j & 1;
+        // every window is one bin; a zero-bin window still emits an all-zero tensor
+        const uint32_t o0 = meta.nb > 0 ? feed.s_off[jb * (kBatchBins + 1)] : 0u;
+        const uint32_t o1 = meta.nb > 0 ? feed.s_off[jb * (kBatchBins + 1) + meta.nb] : 0u;
+        if (staged_once) {
+            if (tid < rows) bulk_wait_read();                      // the previous tensor has left smem
+            __syncthreads();
+        }
+        for (int i = tid; i < n4; i += kEvThreads) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        uint32_t cur = o0;
+        while (cur < o1) {
+            const uint32_t avail = (uint32_t)next_refill * kWsChunkRecords;     // records requested so far
+            const uint32_t limit = o1 < avail ? o1 : avail;
+            const int last_c = (int)((limit - 1) / kWsChunkRecords);
+            while (ready_chunk < last_c) {
+                ++ready_chunk;
+                mbar_wait(full + (ready_chunk % kWsStages), (uint32_t)(ready_chunk / kWsStages) & 1u);
+            }
+            for (uint32_t r = cur + tid; r < limit; r += kEvThreads) {
+                const uint32_t rec = ring[r & (kWsRing - 1)];
+                const uint32_t lp = (rec >> 1) & 0x1FFFu, pol = rec & 1u;
+                const float tn = (float)((double)(rec >> 14) / tp.tw);           // :141, then .float() (:23)
+                const float ts = Kf * tn;                                        // t* = K * t
+                const int c0 = (int)floorf(ts);
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {                                     // centres c0, c0 + 1 (1..K)
+                    const int c = c0 + d;
+                    if (c < 1 || c > K) continue;
+                    const float w = 1.0f - fabsf((float)c - ts);
+                    if (w > 0.0f) atomicAdd(acc + (2 * (c - 1) + (1 - (int)pol)) * pl.P + lp, w);
+                }
+            }
+            cur = limit;
+            if (cur < o1) {                                        // the window outgrew the ring: recycle stages
+                __syncthreads();
+                const int drained = (int)(cur / kWsChunkRecords);
+                if (tid == 0)
+                    for (int r = next_refill; r < drained + kWsStages && r < n_chunks; ++r) issue(r);
+                next_refill = drained + kWsStages;
+            }
+        }
+        __syncthreads();
+        {
+            const int drained = (int)(o1 / kWsChunkRecords);
+            if (drained + kWsStages > next_refill) {
+                if (tid == 0)
+                    for (int r = next_refill; r < drained + kWsStages && r < n_chunks; ++r) issue(r);
+                next_refill = drained + kWsStages;
+            }
+        }
+        if (meta.flags & 2) {
+            float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
+            if (tp.bulk_out) {
+                for (int i = tid; i < n4; i += kEvThreads) {                     // :37  / 5 * 255
+                    float4 v = reinterpret_cast<float4*>(acc)[i];
+                    v.x = __fdiv_rn(v.x, 5.0f) * 255.0f; v.y = __fdiv_rn(v.y, 5.0f) * 255.0f;
+                    v.z = __fdiv_rn(v.z, 5.0f) * 255.0f; v.w = __fdiv_rn(v.w, 5.0f) * 255.0f;
+                    reinterpret_cast<float4*>(acc)[i] = v;
+                }
+                fence_async_smem();
+                feed.publish(j);
+                __syncthreads();
+                if (tid < rows) {
+                    bulk_store_1d(o + (int64_t)tid * HW, acc + tid * pl.P, (uint32_t)npix * 4u);
+                    bulk_commit();
+                }
+                staged_once = true;
+            } else {
+                for (int i = tid; i < rows * pl.P; i += kEvThreads) {
+                    const int row = i / pl.P, lp = i - row * pl.P;
+                    if (lp < npix) __stcs(o + (int64_t)row * HW + lp, __fdiv_rn(acc[i], 5.0f) * 255.0f);
+                }
+                feed.end(j);
+            }
+        } else {
+            feed.end(j);
+        }
+    }
+    if (tp.bulk_out && tid < rows) bulk_wait_all();
+}
+
 // ---- host side -------------------------------------------------------------------------
 struct Layout {
     int P, n_tiles, slots;
@@ -1203,37 +1355,20 @@ static int launch_tiles(const TileParams& tp, int slots, size_t smem, cudaStream
     return EVREP_OK;
 }
 
-}  // namespace evrep
-
-using namespace evrep;
-
-extern "C" {
-
-int64_t evrep_taf_stream_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins, int H, int W) {
-    if (n_events < 0 || n_windows < 0 || total_bins < 0 || H <= 0 || W <= 0) return EVREP_ERR_ARG;
-    Layout L;
-    int rc = make_layout(n_events, n_windows, total_bins, H, W, (int)batches_upper_bound(n_windows, total_bins), L);
-    if (rc) return rc;
-    return L.total;
-}
-
-int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
-                     const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W, int K,
-                     const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
-                     float* state_inout, int emit_state_every_window,
-                     float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
-                     void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream) {
-    if (n_events < 0 || n_windows < 0 || H <= 0 || W <= 0 || abin <= 0 || !state_inout || !scratch) return EVREP_ERR_ARG;
-    if (K != 4 && K != 8) return EVREP_ERR_ARG;
+// Shared front end of the stream entry points: validates the window list, uploads the
+// window / batch tables and runs the bucketing passes.  On return `pl` describes the bucketed
+// records of every (tile, bin).
+static int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+                          const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W,
+                          const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                          void* scratch, int64_t scratch_bytes, cudaStream_t st, StreamPlan& pl, Layout& L) {
     if (xmap && ymap && (sensor_h <= 0 || sensor_w <= 0 || sensor_h > EVREP_COORD_LUT_LEN || sensor_w > EVREP_COORD_LUT_LEN))
         return EVREP_ERR_ARG;
     if ((uint32_t)abin > kDMax) return EVREP_ERR_RANGE;
-    if (n_windows == 0) return EVREP_OK;
-    if (!windows_host || !out || (n_events > 0 && (!t || !x || !y || !p))) return EVREP_ERR_ARG;
-    if ((reinterpret_cast<uintptr_t>(state_inout) & 15) || (reinterpret_cast<uintptr_t>(scratch) & 255)) return EVREP_ERR_ARG;
-    cudaStream_t st = as_stream(stream);
+    if (!windows_host || (n_events > 0 && (!t || !x || !y || !p))) return EVREP_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(scratch) & 255) return EVREP_ERR_ARG;
 
-    // windows -> bins -> batches (host, O(n_windows + bins / 32))
+    // windows -> bins -> batches (host, O(n_windows + bins / 16))
     int64_t TB = 0;
     int64_t prev_end = 0;
     for (int w = 0; w < n_windows; ++w) {
@@ -1262,11 +1397,9 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
             gbin += nb;
         }
     }
-    Layout L;
     int rc = make_layout(n_events, n_windows, TB, H, W, (int)batches.size(), L);
     if (rc) return rc;
     if (scratch_bytes < L.total) return EVREP_ERR_SCRATCH;
-
     // pack and upload the metadata
     std::vector<unsigned char> meta((size_t)L.meta_bytes, 0);
     int64_t* hb = reinterpret_cast<int64_t*>(meta.data() + L.o_wbegin);
@@ -1286,7 +1419,6 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
     EVREP_CUDA(cudaMemcpyAsync(s, meta.data(), (size_t)L.meta_bytes, cudaMemcpyHostToDevice, st));
     // pageable source: the copy has been staged when the call returns, `meta` may die
 
-    StreamPlan pl;
     pl.w_begin = reinterpret_cast<const int64_t*>(s + L.o_wbegin);
     pl.w_end = reinterpret_cast<const int64_t*>(s + L.o_wend);
     pl.w_start = reinterpret_cast<const int64_t*>(s + L.o_wstart);
@@ -1304,12 +1436,6 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
     pl.div_abin = FastDiv::make((uint32_t)abin);
     pl.div_P = FastDiv::make((uint32_t)L.P);
     pl.abin = (uint32_t)abin;
-
-    TileParams tp;
-    tp.pl = pl; tp.state = state_inout; tp.out = out; tp.out_stride = out_stride;
-    tp.emit_state = emit_state_every_window;
-    tp.span = (float)((double)abin + 1e-8);
-    tp.bulk_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
 
     if (TB > 0) {
         EVREP_CUDA(cudaMemsetAsync(s + L.o_counts, 0, (size_t)(L.o_offrel - L.o_counts), st));   // counts + bin_any
@@ -1347,6 +1473,46 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
         EVREP_CUDA(cudaMemsetAsync(s + L.o_tiletotal, 0, (size_t)(L.o_records - L.o_tiletotal), st));
     }
 
+    return EVREP_OK;
+}
+
+}  // namespace evrep
+
+using namespace evrep;
+
+extern "C" {
+
+int64_t evrep_taf_stream_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins, int H, int W) {
+    if (n_events < 0 || n_windows < 0 || total_bins < 0 || H <= 0 || W <= 0) return EVREP_ERR_ARG;
+    Layout L;
+    int rc = make_layout(n_events, n_windows, total_bins, H, W, (int)batches_upper_bound(n_windows, total_bins), L);
+    if (rc) return rc;
+    return L.total;
+}
+
+int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+                     const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W, int K,
+                     const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                     float* state_inout, int emit_state_every_window,
+                     float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
+                     void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream) {
+    if (n_events < 0 || n_windows < 0 || H <= 0 || W <= 0 || abin <= 0 || !state_inout || !scratch) return EVREP_ERR_ARG;
+    if (K != 4 && K != 8) return EVREP_ERR_ARG;
+    if (n_windows == 0) return EVREP_OK;
+    if (!out || (reinterpret_cast<uintptr_t>(state_inout) & 15)) return EVREP_ERR_ARG;
+    cudaStream_t st = as_stream(stream);
+    StreamPlan pl;
+    Layout L;
+    int rc = prepare_stream(t, x, y, p, n_events, windows_host, n_windows, abin, H, W, xmap, ymap, sensor_h, sensor_w,
+                            scratch, scratch_bytes, st, pl, L);
+    if (rc) return rc;
+
+    TileParams tp;
+    tp.pl = pl; tp.state = state_inout; tp.out = out; tp.out_stride = out_stride;
+    tp.emit_state = emit_state_every_window;
+    tp.span = (float)((double)abin + 1e-8);
+    tp.bulk_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+
     const size_t smem = (size_t)TileSmem(L.P, K).total;
     if (ev_tiles_begin) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_begin), st));
     const char* legacy = getenv("EVREP_TAF_TILE_KERNEL");            // "single" = the non-specialised kernel (A/B runs)
@@ -1355,6 +1521,42 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
     else rc = K == 8 ? launch_tiles<8>(tp, L.slots, smem, st) : launch_tiles<4>(tp, L.slots, smem, st);
     if (rc) return rc;
     if (ev_tiles_end) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_end), st));
+    return EVREP_OK;
+}
+
+int64_t evrep_event_volume_stream_scratch_bytes(int64_t n_events, int n_windows, int H, int W) {
+    return evrep_taf_stream_scratch_bytes(n_events, n_windows, n_windows, H, W);
+}
+
+int evrep_event_volume_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+                              const evrep_ev_window* windows_host, int n_windows, int64_t tw, int H, int W, int K,
+                              const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                              float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
+                              evrep_stream_t stream) {
+    if (n_events < 0 || n_windows < 0 || H <= 0 || W <= 0 || tw <= 0 || K < 1 || !scratch) return EVREP_ERR_ARG;
+    if (tw > (int64_t)kDMax) return EVREP_ERR_RANGE;
+    if (n_windows == 0) return EVREP_OK;
+    if (!out || !windows_host) return EVREP_ERR_ARG;
+    cudaStream_t st = as_stream(stream);
+    std::vector<evrep_taf_window> wins((size_t)n_windows);
+    for (int w = 0; w < n_windows; ++w) {
+        wins[w].ev_begin = windows_host[w].ev_begin; wins[w].ev_end = windows_host[w].ev_end;
+        wins[w].start_time = windows_host[w].t0; wins[w].n_bins = 1; wins[w].fresh = 0;
+    }
+    StreamPlan pl;
+    Layout L;
+    int rc = prepare_stream(t, x, y, p, n_events, wins.data(), n_windows, (int)tw, H, W, xmap, ymap, sensor_h, sensor_w,
+                            scratch, scratch_bytes, st, pl, L);
+    if (rc) return rc;
+    const size_t smem = (size_t)EvTileSmem(L.P, K).total;
+    if (smem > 232448) return EVREP_ERR_RANGE;
+    EvTileParams tp;
+    tp.pl = pl; tp.out = out; tp.out_stride = out_stride; tp.tw = (double)tw; tp.K = K;
+    tp.bulk_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   L.P % 4 == 0) ? 1 : 0;
+    EVREP_CUDA(cudaFuncSetAttribute(ev_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ev_tile_kernel<<<L.n_tiles, kEvThreads, smem, st>>>(tp);
+    EVREP_LAUNCH_CHECK();
     return EVREP_OK;
 }
 

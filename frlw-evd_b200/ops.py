@@ -398,3 +398,27 @@ def taf_leaky_u8_batch(volumes, K: int, target_shape=None, maps=None, out=None):
     _lib.call("evrep_taf_leaky_u8_batch", _ptr(volumes), C * H * W, n, K, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
               _stream(volumes.device))
     return out
+
+
+def event_volume_stream(ev: EventStream, windows, tw: int, shape, K: int, maps=None, out=None):
+    """V2: Event Volumes of a list of ordered, non-overlapping windows ``(ev_begin, ev_end, t0)``
+    of common length ``tw`` in one call.  Returns f32 ``[n_windows, 2K, H, W]``."""
+    _need_cuda(ev.t)
+    H, W = shape
+    nw = len(windows)
+    arr = (_lib.EvWindow * nw)()
+    for i, w in enumerate(windows):
+        arr[i] = _lib.EvWindow(int(w[0]), int(w[1]), int(w[2]))
+    if out is None:
+        out = torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=ev.device)
+    assert out.is_contiguous()
+    need = _lib.load().evrep_event_volume_stream_scratch_bytes(ev.n, nw, H, W)
+    if need < 0:
+        _lib.check(int(need), "evrep_event_volume_stream_scratch_bytes")
+    buf = workspace("taf_stream", need, ev.device)
+    xm, ym = _maps(maps)
+    _lib.call("evrep_event_volume_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+              ctypes.cast(arr, ctypes.c_void_p), nw, int(tw), H, W, K, xm, ym,
+              maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W,
+              _ptr(out), 2 * K * H * W, _ptr(buf), buf.numel(), _stream(ev.device))
+    return out

@@ -176,6 +176,28 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
                      void* scratch, int64_t scratch_bytes,
                      void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream);
 
+/* ----------------------------------------- V2: Event Volume, whole streams ----------------
+ * generate_eventvolume.py:15-42 for a list of ordered, non-overlapping windows in one call:
+ * window w holds events [ev_begin, ev_end) and t_norm = (t - t0) / tw (float64, driver :141).
+ * Same two steps as evrep_taf_stream: bucketing by (sensor tile, window) into 4-byte records,
+ * then one CTA per tile that accumulates its [2K, tile] slice in shared memory and writes it
+ * with TMA bulk stores.  out: f32 [n_windows][2K,H,W] (window w at out + w * out_stride).
+ * tw <= 262143 us (use evrep_event_volume per window beyond that); 2K * tile floats must fit
+ * in shared memory (K <= 12 at 512x640). */
+typedef struct {
+    int64_t ev_begin;
+    int64_t ev_end;
+    int64_t t0;
+} evrep_ev_window;
+
+int64_t evrep_event_volume_stream_scratch_bytes(int64_t n_events, int n_windows, int H, int W);
+int evrep_event_volume_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
+                              int64_t n_events, const evrep_ev_window* windows_host, int n_windows,
+                              int64_t tw, int H, int W, int K,
+                              const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                              float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
+                              evrep_stream_t stream);
+
 /* ------------------------------------------------- T3 / R1 / W1: output epilogues ----
  * evrep_nearest_resize: F.interpolate(mode='nearest') as used at generate_taf.py:222 --
  * out[c, Y, X] = in[c, ysrc[Y], xsrc[X]] with the legacy index maps (int32, device).

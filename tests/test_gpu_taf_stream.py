@@ -140,3 +140,31 @@ def test_host_pipeline_matches_single_launch(tmp_path):
     pipe2.run(raw, out2)
     torch.cuda.synchronize()
     assert torch.equal(out2, want)
+
+
+@pytest.mark.parametrize("K", [5, 8])
+def test_event_volume_stream_matches_oracle_and_single_window_path(K):
+    """Whole-stream Event Volume (bucketing + tile kernel) on the gen4 grid: oracle parity on
+    a few windows, and agreement with the per-window CUDA path on all of them."""
+    t, x, y, p = synth.make_stream(720, 1280, 400000, 5e6, 21)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    maps = ops.make_coord_maps((720, 1280), (512, 640), DEV)
+    tw = 50000
+    bounds = [0, 50000, 100000, 100000, 150000, 260000, 310000]       # one empty window, one gap
+    windows = []
+    for a in (0, 50000, 100000, 150000, 260000, 310000):
+        windows.append((idx(t, a), idx(t, a + tw), a))
+    windows.insert(3, (idx(t, 150000), idx(t, 150000), 150000))       # zero events
+    windows.sort(key=lambda w: (w[0], w[1]))
+    got = ops.event_volume_stream(ev, windows, tw, (512, 640), K, maps)
+    for i, (lo, hi, t0) in enumerate(windows):
+        single = ops.event_volume(ev.slice(lo, hi), t0, tw, (512, 640), K, maps)
+        assert close(got[i], single), i
+    from helpers import staged
+    for i in (0, 4):
+        lo, hi, t0 = windows[i]
+        e = staged(t, x, y, p, lo, hi)
+        e[:, 2] = (e[:, 2] - t0) / tw
+        e[:, 0] *= 0.5
+        e[:, 1] *= 512 / 720
+        assert close(got[i], oe.event_volume(e, (512, 640), K)), i

@@ -69,6 +69,12 @@ def main():
                 ops.event_volume(ev.slice(lo, hi), t0, 50000, (H, W), K, maps, out)
         report("event_volume_K%d_50ms_windows" % K, timed(run_ev, args.iters), 9 * n + nw * 8 * K * HW, n)
 
+    for K in (5, 8):
+        outs = torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=dev)
+        report("event_volume_stream_K%d_50ms_windows" % K,
+               timed(lambda: ops.event_volume_stream(ev, windows, 50000, (H, W), K, maps, outs), args.iters),
+               9 * n + nw * 8 * K * HW, n)
+
     def run_eci():
         for lo, hi, _ in windows:
             ops.count_image(ev.slice(lo, hi), (H, W), maps)
