@@ -181,17 +181,22 @@ ev_splat_kernel(Loader ev, TimeNorm<Loader> tn, int64_t n, int H, int W, int K, 
     }
 }
 
+__device__ __forceinline__ float div5_mul255(float v) {      // v / 5 * 255 with a correctly rounded quotient
+    const float q = v * 0.2f;
+    const float r = fmaf(-q, 5.0f, v);
+    return fmaf(r, 0.2f, q) * 255.0f;
+}
+
 __global__ void __launch_bounds__(kBlock)
 ev_scale_kernel(float4* __restrict__ acc4, int64_t n4, float* __restrict__ acc, int64_t n) {   // :37  / 5 * 255
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 v = acc4[i];
-        v.x = __fdiv_rn(v.x, 5.0f) * 255.0f; v.y = __fdiv_rn(v.y, 5.0f) * 255.0f;
-        v.z = __fdiv_rn(v.z, 5.0f) * 255.0f; v.w = __fdiv_rn(v.w, 5.0f) * 255.0f;
+        v.x = div5_mul255(v.x); v.y = div5_mul255(v.y); v.z = div5_mul255(v.z); v.w = div5_mul255(v.w);
         acc4[i] = v;
     }
     for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        acc[i] = __fdiv_rn(acc[i], 5.0f) * 255.0f;
+        acc[i] = div5_mul255(acc[i]);
 }
 
 // ------------------------------------------------------------- T1: TAF, one bin

@@ -1124,10 +1124,20 @@ taf_tile_ws_kernel(TileParams tp) {
 // ---- Event Volume over whole streams ----------------------------------------------------------
 // generate_eventvolume.py:15-42 for a list of non-overlapping windows: the same bucketing (one
 // "bin" per window, d = t - t0) feeds one CTA per sensor tile.  The tile's [2K][P] float
-// accumulator lives in shared memory and doubles as the staging area of the TMA bulk stores:
-// zero -> splat (shared-memory float atomics) -> scale by /5*255 in place -> one bulk store per
-// channel row.  Records arrive through the same ring of TMA bulk copies as in the TAF kernel.
+// accumulator lives in shared memory: splat (shared-memory float atomics), then one pass that
+// reads, clears, scales by /5*255 and stores 16 bytes per thread to the tensor (rows are contiguous).
+// Two CTAs per SM, so one tile's output pass overlaps the other tile's splat.  Records arrive through the same ring of TMA bulk copies as in the TAF kernel.
 constexpr int kEvThreads = 512;
+constexpr int kEvTilesPerSm = 2;        // two CTAs per SM: one splats while the other's bulk store drains
+
+// v / 5 * 255 (generate_eventvolume.py:37) without the IEEE-division subroutine: one Newton
+// correction of v * RN(1/5) is the correctly rounded quotient for every finite v away from the
+// denormal range, so the two roundings of the reference are reproduced.
+__device__ __forceinline__ float div5_mul255(float v) {
+    const float q = v * 0.2f;
+    const float r = fmaf(-q, 5.0f, v);
+    return fmaf(r, 0.2f, q) * 255.0f;
+}
 
 struct EvTileParams {
     StreamPlan pl;
@@ -1150,7 +1160,7 @@ struct EvTileSmem {
     }
 };
 
-__global__ void __launch_bounds__(kEvThreads, 1)
+__global__ void __launch_bounds__(kEvThreads, kEvTilesPerSm)
 ev_tile_kernel(EvTileParams tp) {
     const StreamPlan& pl = tp.pl;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1186,21 +1196,20 @@ ev_tile_kernel(EvTileParams tp) {
     feed.init(smem_raw + lay.feed, &pl, my_off, tid, 0, kEvThreads);       // barrier 0 = the whole CTA
 
     int ready_chunk = -1, next_refill = kWsStages;
-    bool staged_once = false;
     const float Kf = (float)K;
+    const double inv_tw = 1.0 / tp.tw;
     const int n4 = rows * pl.P / 4;
+    const int p4 = pl.P / 4;                                               // float4 columns per row
+    const int row_first = tid / p4, c4_first = tid - row_first * p4;
+    const int row_step = kEvThreads / p4, c4_step = kEvThreads - row_step * p4;
+    for (int i = tid; i < rows * pl.P; i += kEvThreads) acc[i] = 0.0f;     // afterwards the output pass keeps it clean
+    __syncthreads();
     for (int j = 0; j < pl.n_batches; ++j) {
         const Batch meta = feed.begin(j);
         const int jb = j & 1;
         // every window is one bin; a zero-bin window still emits an all-zero tensor
         const uint32_t o0 = meta.nb > 0 ? feed.s_off[jb * (kBatchBins + 1)] : 0u;
         const uint32_t o1 = meta.nb > 0 ? feed.s_off[jb * (kBatchBins + 1) + meta.nb] : 0u;
-        if (staged_once) {
-            if (tid < rows) bulk_wait_read();                      // the previous tensor has left smem
-            __syncthreads();
-        }
-        for (int i = tid; i < n4; i += kEvThreads) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncthreads();
         uint32_t cur = o0;
         while (cur < o1) {
             const uint32_t avail = (uint32_t)next_refill * kWsChunkRecords;     // records requested so far
@@ -1213,7 +1222,10 @@ ev_tile_kernel(EvTileParams tp) {
             for (uint32_t r = cur + tid; r < limit; r += kEvThreads) {
                 const uint32_t rec = ring[r & (kWsRing - 1)];
                 const uint32_t lp = (rec >> 1) & 0x1FFFu, pol = rec & 1u;
-                const float tn = (float)((double)(rec >> 14) / tp.tw);           // :141, then .float() (:23)
+                // (t - t0) / tw in float64 (:141) then .float() (:23): reciprocal + one Newton step
+                const double dd = (double)(rec >> 14);
+                const double q0 = dd * inv_tw;
+                const float tn = (float)fma(fma(-q0, tp.tw, dd), inv_tw, q0);
                 const float ts = Kf * tn;                                        // t* = K * t
                 const int c0 = (int)floorf(ts);
 #pragma unroll
@@ -1243,34 +1255,34 @@ ev_tile_kernel(EvTileParams tp) {
             }
         }
         if (meta.flags & 2) {
+            // read, clear and scale the accumulator (:37  / 5 * 255), 16 bytes per thread straight
+            // to global memory: each row is contiguous, so every warp store is 512 contiguous bytes
             float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
             if (tp.bulk_out) {
-                for (int i = tid; i < n4; i += kEvThreads) {                     // :37  / 5 * 255
+                // (row, column) of float4 number i = tid + k * kEvThreads, advanced without divisions
+                int row = row_first, c4 = c4_first;
+                for (int i = tid; i < n4; i += kEvThreads) {
+                    const int lp = c4 * 4;
                     float4 v = reinterpret_cast<float4*>(acc)[i];
-                    v.x = __fdiv_rn(v.x, 5.0f) * 255.0f; v.y = __fdiv_rn(v.y, 5.0f) * 255.0f;
-                    v.z = __fdiv_rn(v.z, 5.0f) * 255.0f; v.w = __fdiv_rn(v.w, 5.0f) * 255.0f;
-                    reinterpret_cast<float4*>(acc)[i] = v;
+                    reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lp < npix) {
+                        v.x = div5_mul255(v.x); v.y = div5_mul255(v.y); v.z = div5_mul255(v.z); v.w = div5_mul255(v.w);
+                        __stcs(reinterpret_cast<float4*>(o + (int64_t)row * HW + lp), v);
+                    }
+                    row += row_step; c4 += c4_step;
+                    if (c4 >= p4) { c4 -= p4; ++row; }
                 }
-                fence_async_smem();
-                feed.publish(j);
-                __syncthreads();
-                if (tid < rows) {
-                    bulk_store_1d(o + (int64_t)tid * HW, acc + tid * pl.P, (uint32_t)npix * 4u);
-                    bulk_commit();
-                }
-                staged_once = true;
             } else {
                 for (int i = tid; i < rows * pl.P; i += kEvThreads) {
                     const int row = i / pl.P, lp = i - row * pl.P;
-                    if (lp < npix) __stcs(o + (int64_t)row * HW + lp, __fdiv_rn(acc[i], 5.0f) * 255.0f);
+                    const float v = acc[i];
+                    acc[i] = 0.0f;
+                    if (lp < npix) __stcs(o + (int64_t)row * HW + lp, div5_mul255(v));
                 }
-                feed.end(j);
             }
-        } else {
-            feed.end(j);
         }
+        feed.end(j);                                               // also orders the clears before the next splat
     }
-    if (tp.bulk_out && tid < rows) bulk_wait_all();
 }
 
 // ---- host side -------------------------------------------------------------------------
@@ -1283,9 +1295,10 @@ struct Layout {
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
-static int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n_batches, Layout& L) {
+static int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n_batches, Layout& L,
+                       int tiles_per_sm = 1) {
     const int64_t HW = (int64_t)H * W;
-    const int sms = sm_count();
+    const int sms = sm_count() * tiles_per_sm;
     int64_t P = (HW + sms - 1) / sms;
     P = (P + 31) / 32 * 32;
     if (P > kTafThreads * kMaxSlots) P = kTafThreads * kMaxSlots;
@@ -1361,7 +1374,8 @@ static int launch_tiles(const TileParams& tp, int slots, size_t smem, cudaStream
 static int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
                           const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W,
                           const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
-                          void* scratch, int64_t scratch_bytes, cudaStream_t st, StreamPlan& pl, Layout& L) {
+                          void* scratch, int64_t scratch_bytes, cudaStream_t st, StreamPlan& pl, Layout& L,
+                          int tiles_per_sm = 1) {
     if (xmap && ymap && (sensor_h <= 0 || sensor_w <= 0 || sensor_h > EVREP_COORD_LUT_LEN || sensor_w > EVREP_COORD_LUT_LEN))
         return EVREP_ERR_ARG;
     if ((uint32_t)abin > kDMax) return EVREP_ERR_RANGE;
@@ -1397,7 +1411,7 @@ static int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* 
             gbin += nb;
         }
     }
-    int rc = make_layout(n_events, n_windows, TB, H, W, (int)batches.size(), L);
+    int rc = make_layout(n_events, n_windows, TB, H, W, (int)batches.size(), L, tiles_per_sm);
     if (rc) return rc;
     if (scratch_bytes < L.total) return EVREP_ERR_SCRATCH;
     // pack and upload the metadata
@@ -1525,7 +1539,11 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
 }
 
 int64_t evrep_event_volume_stream_scratch_bytes(int64_t n_events, int n_windows, int H, int W) {
-    return evrep_taf_stream_scratch_bytes(n_events, n_windows, n_windows, H, W);
+    if (n_events < 0 || n_windows < 0 || H <= 0 || W <= 0) return EVREP_ERR_ARG;
+    Layout L;
+    int rc = make_layout(n_events, n_windows, n_windows, H, W, (int)batches_upper_bound(n_windows, n_windows), L, kEvTilesPerSm);
+    if (rc) return rc;
+    return L.total;
 }
 
 int evrep_event_volume_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
@@ -1546,7 +1564,7 @@ int evrep_event_volume_stream(const uint32_t* t, const uint16_t* x, const uint16
     StreamPlan pl;
     Layout L;
     int rc = prepare_stream(t, x, y, p, n_events, wins.data(), n_windows, (int)tw, H, W, xmap, ymap, sensor_h, sensor_w,
-                            scratch, scratch_bytes, st, pl, L);
+                            scratch, scratch_bytes, st, pl, L, kEvTilesPerSm);
     if (rc) return rc;
     const size_t smem = (size_t)EvTileSmem(L.P, K).total;
     if (smem > 232448) return EVREP_ERR_RANGE;
