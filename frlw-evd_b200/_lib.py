@@ -39,6 +39,9 @@ SIGNATURES = {
     "evrep_count_accumulate_aos64": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
     "evrep_count_finalize": (c_int, [P, c_int, c_int, P, c_int, P]),
     "evrep_count_image": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P, P]),
+    "evrep_count_images_u8": (c_int, [P, P, P, c_int64, P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P]),
+    "evrep_sae_u8": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, P, c_int, c_int, P, P, c_float, c_float, P, c_int,
+                             P, P, P, P, P]),
     "evrep_sae": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, P, c_float, c_float, P, c_int, P, P, P, P, P]),
     "evrep_sae_aos64": (c_int, [P, c_int64, c_int, c_int, c_int, c_float, c_float, P, c_int, P, P, P, P, P]),
     "evrep_event_volume": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, c_int, P, P, P, P]),

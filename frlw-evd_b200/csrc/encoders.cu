@@ -88,6 +88,23 @@ count_finalize_kernel(uint32_t* __restrict__ counts, int64_t cells, float* __res
     }
 }
 
+// Count LUT + nearest resize + uint8 truncation in one pass (driver epilogue,
+// generate_eventcountimage.py:164,180): out[c, Y, X] = u8(LUT[count[c, ysrc[Y], xsrc[X]]]).
+__global__ void __launch_bounds__(kBlock)
+count_finalize_u8_kernel(const uint32_t* __restrict__ counts, int H, int W, int Ht, int Wt,
+                         const int32_t* __restrict__ ysrc, const int32_t* __restrict__ xsrc, uint8_t* __restrict__ out) {
+    const int64_t total = (int64_t)2 * Ht * Wt;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int X = (int)(i % Wt);
+        const int64_t r = i / Wt;
+        const int Y = (int)(r % Ht), c = (int)(r / Ht);
+        const int ys = ysrc ? ysrc[Y] : Y, xs = xsrc ? xsrc[X] : X;
+        const uint32_t n = counts[((int64_t)c * H + ys) * W + xs];
+        out[i] = (uint8_t)(int)c_count_lut[n < 32u ? n : 32u];
+    }
+}
+
 // ------------------------------------------------------------------ A1: SAE
 // Order-preserving float <-> u32 key (0 is reserved for "no event").
 __device__ __forceinline__ uint32_t float_key(float f) {
@@ -128,6 +145,7 @@ sae_scatter_kernel(Loader ev, int64_t n, int H, int W, uint32_t* __restrict__ ke
 }
 
 struct Lambdas { float v[8]; };
+__device__ __forceinline__ uint8_t to_u8_trunc(float v) { return (uint8_t)(int)v; }   // numpy astype(uint8)
 
 // :48 init, :51-54 max-merge with memory + state write, :55-63 the L decays, fused.
 __global__ void __launch_bounds__(kBlock)
@@ -143,6 +161,39 @@ sae_finalize_kernel(uint32_t* __restrict__ keys, int64_t cells, float init, floa
         mem_out[i] = latest;
         float rel = latest - now_f32;
         for (int l = 0; l < L; ++l) out[(int64_t)l * cells + i] = expf(lam.v[l] * rel) * 255.0f;
+    }
+}
+
+// SAE epilogue for the drivers (generate_surfaceofactiveevents.py:186-204): the state is
+// updated at grid resolution and the L decays are written resized + truncated to uint8,
+// out[l, p, Y, X].  Output cells recompute `latest` from (keys, memory_in), so the two halves
+// of the index space do not depend on each other; `keys` is cleared by the caller afterwards.
+__global__ void __launch_bounds__(kBlock)
+sae_finalize_u8_kernel(const uint32_t* __restrict__ keys, int H, int W, int Ht, int Wt,
+                       const int32_t* __restrict__ ysrc, const int32_t* __restrict__ xsrc, float init, float now_f32,
+                       Lambdas lam, int L, const float* __restrict__ mem_in, float* __restrict__ mem_out,
+                       uint8_t* __restrict__ out) {
+    const int64_t cells = (int64_t)2 * H * W, tcells = (int64_t)2 * Ht * Wt;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells + tcells; i += stride) {
+        if (i < cells) {
+            const uint32_t k = keys[i];
+            float latest = k ? key_float(k) : init;
+            if (mem_in) { const float m = mem_in[i]; latest = latest > m ? latest : m; }
+            mem_out[i] = latest;
+        } else {
+            const int64_t j = i - cells;
+            const int X = (int)(j % Wt);
+            const int64_t r = j / Wt;
+            const int Y = (int)(r % Ht), p = (int)(r / Ht);
+            const int ys = ysrc ? ysrc[Y] : Y, xs = xsrc ? xsrc[X] : X;
+            const int64_t src = ((int64_t)p * H + ys) * W + xs;
+            const uint32_t k = keys[src];
+            float latest = k ? key_float(k) : init;
+            if (mem_in) { const float m = mem_in[src]; latest = latest > m ? latest : m; }
+            const float rel = latest - now_f32;
+            for (int l = 0; l < L; ++l) out[(int64_t)l * tcells + j] = to_u8_trunc(expf(lam.v[l] * rel) * 255.0f);
+        }
     }
 }
 
@@ -495,6 +546,58 @@ int evrep_count_image(const uint16_t* x, const uint16_t* y, const uint8_t* p, in
     int rc = evrep_count_accumulate(x, y, p, n, H, W, xmap, ymap, counts, stream);
     if (rc) return rc;
     return evrep_count_finalize(counts, H, W, out, 1, stream);
+}
+
+int evrep_count_images_u8(const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n, const int64_t* sizes_host,
+                          int n_sizes, int H, int W, const uint16_t* xmap, const uint16_t* ymap, int Ht, int Wt,
+                          const int32_t* ysrc, const int32_t* xsrc, uint32_t* counts, uint8_t* out, evrep_stream_t stream) {
+    if (H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0 || n < 0 || n_sizes <= 0 || !sizes_host || !counts || !out) return EVREP_ERR_ARG;
+    if (n > 0 && (!x || !y || !p)) return EVREP_ERR_ARG;
+    if ((!ysrc || !xsrc) && (Ht != H || Wt != W)) return EVREP_ERR_ARG;
+    int rc = ensure_count_lut();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    int64_t done = 0;
+    const int64_t per = (int64_t)2 * Ht * Wt;
+    for (int i = 0; i < n_sizes; ++i) {
+        if (i > 0 && sizes_host[i] < sizes_host[i - 1]) return EVREP_ERR_ARG;
+        const int64_t take = sizes_host[i] < n ? sizes_host[i] : n;          // events[-N:]
+        if (take > done) {                                                   // only the events not counted yet
+            const int64_t lo = n - take, cnt = take - done;
+            SoA ev{nullptr, x + lo, y + lo, p + lo, xmap, ymap};
+            count_accumulate_kernel<SoA><<<grid_for(cnt, 4), kBlock, 0, st>>>(ev, cnt, H, W, counts);
+            EVREP_LAUNCH_CHECK();
+            done = take;
+        }
+        count_finalize_u8_kernel<<<grid_for(per), kBlock, 0, st>>>(counts, H, W, Ht, Wt, ysrc, xsrc, out + i * per);
+        EVREP_LAUNCH_CHECK();
+    }
+    EVREP_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * 2 * (size_t)H * W, st));
+    return EVREP_OK;
+}
+
+int evrep_sae_u8(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n, int H, int W,
+                 const uint16_t* xmap, const uint16_t* ymap, int Ht, int Wt, const int32_t* ysrc, const int32_t* xsrc,
+                 float init, float now_f32, const float* lambdas_host, int L, const float* memory_in, float* memory_out,
+                 uint32_t* keys, uint8_t* out, evrep_stream_t stream) {
+    if (H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0 || L < 1 || L > 8 || !lambdas_host || !memory_out || !keys || !out || n < 0)
+        return EVREP_ERR_ARG;
+    if (n > 0 && (!t || !x || !y || !p)) return EVREP_ERR_ARG;
+    if ((!ysrc || !xsrc) && (Ht != H || Wt != W)) return EVREP_ERR_ARG;
+    if (memory_in == memory_out) return EVREP_ERR_ARG;         // output cells re-read memory_in
+    cudaStream_t st = as_stream(stream);
+    if (n > 0) {
+        SoA ev{t, x, y, p, xmap, ymap};
+        sae_scatter_kernel<SoA><<<grid_for(n, 4), kBlock, 0, st>>>(ev, n, H, W, keys);
+        EVREP_LAUNCH_CHECK();
+    }
+    Lambdas lam;
+    for (int l = 0; l < 8; ++l) lam.v[l] = l < L ? lambdas_host[l] : 0.0f;
+    sae_finalize_u8_kernel<<<grid_for((int64_t)2 * H * W + (int64_t)2 * Ht * Wt), kBlock, 0, st>>>(
+        keys, H, W, Ht, Wt, ysrc, xsrc, init, now_f32, lam, L, memory_in, memory_out, out);
+    EVREP_LAUNCH_CHECK();
+    EVREP_CUDA(cudaMemsetAsync(keys, 0, sizeof(uint32_t) * 2 * (size_t)H * W, st));
+    return EVREP_OK;
 }
 
 int evrep_sae(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n, int H, int W,

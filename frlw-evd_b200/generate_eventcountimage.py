@@ -45,8 +45,9 @@ def encode_recording(rec: DeviceRecording, labels, geom: Geometry, sizes):
         if end_count is None:
             continue
         lo = max(end_count - max(sizes), 0)
-        frames = ops.count_images_nested(rec.events.slice(lo, end_count), sizes, geom.grid, geom.coord_maps)
-        yield label, [ops.quantize_u8(geom.to_target(f)) for f in frames]
+        u8 = ops.count_images_u8(rec.events.slice(lo, end_count), sizes, geom.grid, geom.target, geom.coord_maps,
+                                 geom.resize_maps)
+        yield label, list(u8)
 
 
 def main(argv=None):

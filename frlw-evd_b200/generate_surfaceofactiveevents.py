@@ -49,7 +49,6 @@ def encode_recording(rec: DeviceRecording, labels, geom: Geometry, mode="train")
     """Yield ``(label, u8 [L,2,Ht,Wt])`` (:147-213)."""
     loader = rec.loader
     t_upper, c_upper, memory = -100000000, 0, None
-    L = len(LAMDAS)
     for label in labels:
         end_time = int(label)
         end_count = loader.seek_time(end_time)
@@ -62,13 +61,11 @@ def encode_recording(rec: DeviceRecording, labels, geom: Geometry, mode="train")
         if start_time <= t_upper:
             start_count = c_upper
         t_upper, c_upper = label, end_count
-        keep = None
+        u8 = None
         for tw in (TIME_WINDOW if mode == "test" else [max(TIME_WINDOW)]):
             lo = loader.upper_index(end_time - tw, start_count, end_count)     # events[:, 2] > end_time - tw
-            vol, memory = ops.sae(rec.events.slice(lo, end_count), geom.grid, LAMDAS, memory, label, geom.coord_maps)
-            if tw == max(TIME_WINDOW):
-                keep = vol
-        u8 = ops.quantize_u8(geom.to_target(keep)).view(L, 2, geom.target[0], geom.target[1])
+            u8, memory = ops.sae_u8(rec.events.slice(lo, end_count), geom.grid, geom.target, LAMDAS, memory, label,
+                                    geom.coord_maps, geom.resize_maps)         # the largest window comes last
         yield label, u8
 
 

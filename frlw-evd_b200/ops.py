@@ -422,3 +422,45 @@ def event_volume_stream(ev: EventStream, windows, tw: int, shape, K: int, maps=N
               maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W,
               _ptr(out), 2 * K * H * W, _ptr(buf), buf.numel(), _stream(ev.device))
     return out
+
+
+def count_images_u8(ev: EventStream, sizes: Sequence[int], shape, target_shape, maps=None, resize_maps=None, out=None):
+    """Driver form of the count image: the nested last-N windows of one label as uint8
+    ``[len(sizes), 2, Ht, Wt]`` in one library call (LUT + nearest resize + truncation fused)."""
+    _need_cuda(ev.x)
+    H, W = shape
+    Ht, Wt = target_shape
+    sizes = [int(v) for v in sizes]
+    arr = (ctypes.c_int64 * len(sizes))(*sizes)
+    if (Ht, Wt) != (H, W) and resize_maps is None:
+        resize_maps = nearest_maps((H, W), (Ht, Wt), ev.device)
+    ys, xs = resize_maps if (Ht, Wt) != (H, W) else (None, None)
+    if out is None:
+        out = torch.empty((len(sizes), 2, Ht, Wt), dtype=torch.uint8, device=ev.device)
+    counts = scratch("count", 8 * H * W, ev.device)
+    xm, ym = _maps(maps)
+    _lib.call("evrep_count_images_u8", _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, ctypes.cast(arr, ctypes.c_void_p),
+              len(sizes), H, W, xm, ym, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(counts), _ptr(out), _stream(ev.device))
+    return out
+
+
+def sae_u8(ev: EventStream, shape, target_shape, lambdas, memory, now, maps=None, resize_maps=None, out=None):
+    """Driver form of the SAE: ``(uint8 [L,2,Ht,Wt], new memory f32 [2,H,W])`` in one library call."""
+    _need_cuda(ev.t, memory)
+    H, W = shape
+    Ht, Wt = target_shape
+    L = len(lambdas)
+    lam = (ctypes.c_float * L)(*[float(np.float32(v)) for v in lambdas])
+    init, now_f32 = _sae_scalars(now)
+    if (Ht, Wt) != (H, W) and resize_maps is None:
+        resize_maps = nearest_maps((H, W), (Ht, Wt), ev.device)
+    ys, xs = resize_maps if (Ht, Wt) != (H, W) else (None, None)
+    if out is None:
+        out = torch.empty((L, 2, Ht, Wt), dtype=torch.uint8, device=ev.device)
+    mem_out = torch.empty((2, H, W), dtype=torch.float32, device=ev.device)
+    keys = scratch("sae", 8 * H * W, ev.device)
+    xm, ym = _maps(maps)
+    _lib.call("evrep_sae_u8", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, H, W, xm, ym, Ht, Wt, _ptr(ys), _ptr(xs),
+              init, now_f32, ctypes.cast(lam, ctypes.c_void_p), L, _ptr(memory), _ptr(mem_out), _ptr(keys), _ptr(out),
+              _stream(ev.device))
+    return out, mem_out

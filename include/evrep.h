@@ -85,6 +85,17 @@ int evrep_count_image(const uint16_t* x, const uint16_t* y, const uint8_t* p, in
                       int H, int W, const uint16_t* xmap, const uint16_t* ymap,
                       uint32_t* counts, float* out, evrep_stream_t stream);
 
+/* Driver epilogue fused (generate_eventcountimage.py:156-180): the nested last-N windows of one
+ * label -- sizes_host ascending, window i = the last min(sizes[i], n) of the n events given -- each
+ * event counted once, every window written as uint8 [2,Ht,Wt] (count LUT, nearest resize with the
+ * int32 maps ysrc/xsrc or NULL when Ht x Wt == H x W, truncation) into out + i * 2*Ht*Wt.
+ * `counts` zero on entry, zero on return. */
+int evrep_count_images_u8(const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n,
+                          const int64_t* sizes_host, int n_sizes, int H, int W,
+                          const uint16_t* xmap, const uint16_t* ymap, int Ht, int Wt,
+                          const int32_t* ysrc, const int32_t* xsrc, uint32_t* counts, uint8_t* out,
+                          evrep_stream_t stream);
+
 /* ------------------------------------------------- A1: Surface of Active Events ------
  * generate_surfaceofactiveevents.py:71-80 (generate_leaky_cuda) + :44-69 (taf_cuda).
  * latest[p,y,x] = max float32(t) over the events (the sequential last-writer result for
@@ -98,6 +109,14 @@ int evrep_sae(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uin
               float init, float now_f32, const float* lambdas_host, int L,
               const float* memory_in, float* memory_out, uint32_t* keys, float* out,
               evrep_stream_t stream);
+/* evrep_sae with the driver epilogue fused (generate_surfaceofactiveevents.py:186-204): the state
+ * (memory_out, f32 [2,H,W], must not alias memory_in) is updated at grid resolution and the decays
+ * are written resized + truncated as uint8 [L,2,Ht,Wt]. */
+int evrep_sae_u8(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n,
+                 int H, int W, const uint16_t* xmap, const uint16_t* ymap, int Ht, int Wt,
+                 const int32_t* ysrc, const int32_t* xsrc, float init, float now_f32,
+                 const float* lambdas_host, int L, const float* memory_in, float* memory_out,
+                 uint32_t* keys, uint8_t* out, evrep_stream_t stream);
 int evrep_sae_aos64(const double* events, int64_t n, int ncols, int H, int W,
                     float init, float now_f32, const float* lambdas_host, int L,
                     const float* memory_in, float* memory_out, uint32_t* keys, float* out,
