@@ -76,6 +76,7 @@ struct StreamPlan {       // device pointers into the scratch buffer
     uint32_t* tile_total; // [n_tiles]
     uint32_t* tile_base;  // [n_tiles+1] (multiples of 4 records: 16-byte aligned lists)
     uint32_t* records;    // [n_events + 4 n_tiles]
+    uint32_t* tile_bits;  // [n_tiles][n_batches]: per batch, bit b = tile has records in bin b, bit 16+b = bin is non-empty anywhere
     int n_windows, n_batches, TB, n_tiles, P, H, W;
     FastDiv div_abin, div_P;
     uint32_t abin;
@@ -447,6 +448,24 @@ taf_scan_tiles_kernel(StreamPlan pl) {         // n_tiles <= kMaxTiles = 2 * 102
     }
 }
 
+// Per (tile, batch) summary for the consumer warps of the tile kernel: which bins of the batch
+// have records of this tile (bit b) and which are non-empty anywhere (bit 16 + b).
+static_assert(kBatchBins <= 16, "two 16-bit masks per batch");
+__global__ void __launch_bounds__(256)
+taf_tile_bits_kernel(StreamPlan pl) {
+    const int tile = blockIdx.x;
+    const uint32_t* off = pl.off_rel + (int64_t)tile * (pl.TB + 1);
+    for (int j = threadIdx.x; j < pl.n_batches; j += blockDim.x) {
+        const Batch m = pl.batches[j];
+        uint32_t bits = 0;
+        for (int b = 0; b < m.nb; ++b) {
+            if (off[m.gbin0 + b + 1] > off[m.gbin0 + b]) bits |= 1u << b;
+            if (pl.bin_any[m.gbin0 + b]) bits |= 1u << (16 + b);
+        }
+        pl.tile_bits[(int64_t)tile * pl.n_batches + j] = bits;
+    }
+}
+
 // ---- mbarrier / TMA bulk-copy primitives (PTX) --------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -485,6 +504,7 @@ struct TileParams {
     float* out;            // window w at out + w * out_stride
     int64_t out_stride;
     int emit_state;        // write the state after every window (always after the last)
+    int n_emits;           // number of windows (batches that end a window)
     int bulk_out;          // out rows are 16-byte aligned: emit through smem + TMA bulk stores
     float span;            // f32(abin + 1e-8)
 };
@@ -752,15 +772,19 @@ taf_tile_kernel(TileParams tp) {
 // ---- warp-specialised tile kernel -------------------------------------------------------------
 // Same algorithm as taf_tile_kernel, split into two roles so that the latency-bound record
 // bookkeeping runs ahead of, and concurrently with, the arithmetic:
-//   * producer warpgroup (warps 0-3, 56 registers after setmaxnreg.dec): walks the bins, waits for
-//     the TMA ring, accumulates (n, sum d) of bin b+1 into one of two accumulator buffers, refills
-//     the ring;
+//   * producer warpgroup (warps 0-3, 56 registers after setmaxnreg.dec).  Three accumulate warps
+//     walk the bins, wait for the TMA ring, accumulate (n, sum d) of the next bins into one of two
+//     accumulator buffers and refill the ring; the fourth, the store warp, sends every staged
+//     window tensor with TMA bulk stores;
 //   * consumer warpgroups (warps 4-15, 152 registers after setmaxnreg.inc): own the FIFO state of
-//     the tile (6 pixels per thread), read + clear the accumulator of bin b, apply the update, and
-//     emit the window tensor through the staging tile + TMA bulk stores.
-// Hand-over uses named barriers (bar.arrive / bar.sync): FULL[buf] producer -> consumer,
-// EMPTY[buf] consumer -> producer.  4 warps per SM sub-partition: 1 producer + 3 consumers.
-constexpr int kProducerThreads = 128;
+//     the tile (6 pixels per thread), read + clear the accumulator of a bin, apply the update, and
+//     copy the window tensor into the staging tile.  They never synchronise among themselves.
+// Hand-over uses named barriers (bar.arrive / bar.sync): FULL[buf] accumulate -> consumers,
+// EMPTY[buf] consumers -> accumulate, STAGED consumers -> store warp, STAGE_FREE store warp ->
+// consumers.  4 warps per SM sub-partition: 1 producer-group warp + 3 consumers.
+constexpr int kProducerThreads = 128;   // the producer warpgroup: 3 accumulate warps + 1 store warp
+constexpr int kAccumThreads = 96;
+constexpr int kStoreThreads = 32;
 constexpr int kConsumerThreads = 384;
 constexpr int kWsThreads = kProducerThreads + kConsumerThreads;
 constexpr int kWsChunkRecords = 512;    // 2 KB TMA bulk copies
@@ -768,13 +792,13 @@ constexpr int kWsStages = 8;            // 16 KB ring = a flat circular buffer o
 constexpr int kWsRing = kWsChunkRecords * kWsStages;
 static_assert((kWsRing & (kWsRing - 1)) == 0, "ring size must be a power of two");
 
-enum : int { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarConsumers = 5, kBarProducers = 6 };
+enum : int { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarProducers = 6, kBarStaged = 7, kBarStageFree = 8 };
 
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 struct TileSmemWS {
-    int ring, acc, stage, bars, feed_p, feed_c, total;
+    int ring, acc, stage, bars, feed_p, total;
     static constexpr int kFeedBytes = 2 * (kBatchBins + 1) * 4 + 2 * kBatchBins * 4 + 2 * (int)sizeof(Batch) + 8;
     __host__ __device__ TileSmemWS(int P, int K) {
         int o = 0;
@@ -783,7 +807,6 @@ struct TileSmemWS {
         stage = o;  o += 2 * K * P * 4;                             // [2K][P] output staging
         bars = o;   o += 64;
         feed_p = o; o += (kFeedBytes + 15) / 16 * 16;
-        feed_c = o; o += (kFeedBytes + 15) / 16 * 16;
         total = o;
     }
 };
@@ -862,12 +885,35 @@ taf_tile_ws_kernel(TileParams tp) {
     __syncthreads();
 
     if (tid < kProducerThreads) {
-        // ================================ producer warpgroup ================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (tid >= kAccumThreads) {
+            // ================================== store warp ==================================
+            // Waits for the consumers to stage a window tensor, sends its rows with TMA bulk
+            // stores and tells the consumers when the staging tile may be overwritten.
+            if (!tp.bulk_out) return;
+            const int lane = tid - kAccumThreads;
+            int emitted = 0;
+            for (int j = 0; j < pl.n_batches; ++j) {
+                const Batch m = pl.batches[j];
+                if (!(m.flags & 2)) continue;
+                named_sync(kBarStaged, kStoreThreads + kConsumerThreads);
+                if (lane < 2 * K) {
+                    float* o = tp.out + (int64_t)m.win * tp.out_stride + pix0;
+                    bulk_store_1d(o + (int64_t)lane * HW, stage + lane * pl.P, (uint32_t)npix * 4u);
+                    bulk_commit();
+                    bulk_wait_read();                                // the rows have left shared memory
+                }
+                __syncwarp();
+                if (++emitted < tp.n_emits) named_arrive(kBarStageFree, kStoreThreads + kConsumerThreads);
+            }
+            if (lane < 2 * K) bulk_wait_all();
+            return;
+        }
+        // ================================ accumulate warps ================================
         const uint32_t* my_records = pl.records + pl.tile_base[tile];
         const uint32_t list_len = (pl.tile_total[tile] + 3u) & ~3u;
         const int n_chunks = (int)((list_len + kWsChunkRecords - 1) / kWsChunkRecords);
-        auto issue = [&](int c) {           // producer thread 0 only
+        auto issue = [&](int c) {           // thread 0 only
             const uint32_t first = (uint32_t)c * kWsChunkRecords;
             const uint32_t bytes = min((uint32_t)kWsChunkRecords, list_len - first) * 4u;
             uint64_t* bar = full + (c % kWsStages);
@@ -877,9 +923,10 @@ taf_tile_ws_kernel(TileParams tp) {
         if (tid == 0)
             for (int c = 0; c < n_chunks && c < kWsStages; ++c) issue(c);
         BatchFeed feed;
-        feed.init(smem_raw + lay.feed_p, &pl, my_off, tid, kBarProducers, kProducerThreads);
+        feed.init(smem_raw + lay.feed_p, &pl, my_off, tid, kBarProducers, kAccumThreads);
         int ready_chunk = -1, next_refill = kWsStages, buf = 0;
         int uses0 = 0, uses1 = 0;
+        constexpr int kHandOver = kAccumThreads + kConsumerThreads;
         for (int j = 0; j < pl.n_batches; ++j) {
             const Batch meta = feed.begin(j);
             const int jb = j & 1;
@@ -901,14 +948,14 @@ taf_tile_ws_kernel(TileParams tp) {
                     uint32_t pre[kPre];
 #pragma unroll
                     for (int i = 0; i < kPre; ++i) {
-                        const uint32_t r = o0 + tid + i * kProducerThreads;
+                        const uint32_t r = o0 + tid + i * kAccumThreads;
                         pre[i] = r < o1 ? ring[r & (kWsRing - 1)] : kNoRec;
                     }
-                    const bool all_pre = (o1 - o0) <= (uint32_t)(kPre * kProducerThreads);
+                    const bool all_pre = (o1 - o0) <= (uint32_t)(kPre * kAccumThreads);
                     // the consumers must have drained this buffer (its first use needs no wait); the
-                    // barrier also tells that every producer thread is done with all earlier bins
-                    if (had_use) named_sync(kBarEmpty0 + buf, kWsThreads);
-                    else named_sync(kBarProducers, kProducerThreads);
+                    // barrier also tells that every accumulate thread is done with all earlier bins
+                    if (had_use) named_sync(kBarEmpty0 + buf, kHandOver);
+                    else named_sync(kBarProducers, kAccumThreads);
                     {
                         // ring stages whose chunk ends before the first record still to be read are free
                         const int drained = (int)((all_pre ? o1 : o0) / kWsChunkRecords);
@@ -924,7 +971,7 @@ taf_tile_ws_kernel(TileParams tp) {
                             atomicAdd(&cell->y, pre[i] >> 14);
                         }
                     }
-                    for (uint32_t r = o0 + tid + kPre * kProducerThreads; r < o1; r += kProducerThreads) {
+                    for (uint32_t r = o0 + tid + kPre * kAccumThreads; r < o1; r += kAccumThreads) {
                         const uint32_t rec = ring[r & (kWsRing - 1)];
                         uint2* cell = my_acc + (rec & 0x3FFFu);
                         atomicAdd(&cell->x, 1u);
@@ -932,14 +979,14 @@ taf_tile_ws_kernel(TileParams tp) {
                     }
                 } else {
                     // a single bin longer than the ring: go chunk by chunk, recycling drained stages
-                    if (had_use) named_sync(kBarEmpty0 + buf, kWsThreads);
+                    if (had_use) named_sync(kBarEmpty0 + buf, kHandOver);
                     uint32_t cur = o0;
                     while (cur < o1) {
                         const int c = (int)(cur / kWsChunkRecords);
                         const uint32_t chunk_end = (uint32_t)(c + 1) * kWsChunkRecords;
                         const uint32_t seg_end = o1 < chunk_end ? o1 : chunk_end;
                         if (c >= next_refill) {
-                            named_sync(kBarProducers, kProducerThreads);
+                            named_sync(kBarProducers, kAccumThreads);
                             if (tid == 0)
                                 for (int r = next_refill; r <= c && r < n_chunks; ++r) issue(r);
                             next_refill = c + 1;
@@ -948,7 +995,7 @@ taf_tile_ws_kernel(TileParams tp) {
                             ++ready_chunk;
                             mbar_wait(full + (ready_chunk % kWsStages), (uint32_t)(ready_chunk / kWsStages) & 1u);
                         }
-                        for (uint32_t r = cur + tid; r < seg_end; r += kProducerThreads) {
+                        for (uint32_t r = cur + tid; r < seg_end; r += kAccumThreads) {
                             const uint32_t rec = ring[r & (kWsRing - 1)];
                             uint2* cell = my_acc + (rec & 0x3FFFu);
                             atomicAdd(&cell->x, 1u);
@@ -957,21 +1004,22 @@ taf_tile_ws_kernel(TileParams tp) {
                         cur = seg_end;
                     }
                 }
-                named_arrive(kBarFull0 + buf, kWsThreads);           // hand the accumulator to the consumers
+                named_arrive(kBarFull0 + buf, kHandOver);            // hand the accumulator to the consumers
                 if (buf) ++uses1; else ++uses0;
                 buf ^= 1;
             }
             feed.end(j);
         }
         // match the consumers' last EMPTY arrivals so that no barrier phase is left open
-        if (uses0 > 0) named_sync(kBarEmpty0, kWsThreads);
-        if (uses1 > 0) named_sync(kBarEmpty1, kWsThreads);
+        if (uses0 > 0) named_sync(kBarEmpty0, kHandOver);
+        if (uses1 > 0) named_sync(kBarEmpty1, kHandOver);
         return;
     }
 
     // =================================== consumer warpgroups ===================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int ctid = tid - kProducerThreads;
+    constexpr int kHandOver = kAccumThreads + kConsumerThreads;
     static_assert(K % 4 == 0, "K must be a multiple of 4");
     float2 v[SLOTS][2][K / 2];
     const bool first_fresh = (pl.batches[0].flags & 1) != 0;
@@ -993,14 +1041,17 @@ taf_tile_ws_kernel(TileParams tp) {
                 for (int k = 0; k < K / 2; ++k) v[s][p][k] = make_float2(kTafInit, kTafInit);
         }
     }
-    BatchFeed feed;
-    feed.init(smem_raw + lay.feed_c, &pl, my_off, ctid, kBarConsumers, kConsumerThreads);
-    int buf = 0;
-    bool staged_once = false;
+    // batch descriptors and the tile's per-batch bit masks come straight from global memory,
+    // one batch ahead: the consumers never synchronise among themselves
+    const uint32_t* my_bits = pl.tile_bits + (int64_t)tile * pl.n_batches;
+    Batch meta = pl.batches[0];
+    uint32_t bits = my_bits[0];
+    int buf = 0, emitted = 0;
     const float2 minus1 = make_float2(-1.0f, -1.0f);
     for (int j = 0; j < pl.n_batches; ++j) {
-        const Batch meta = feed.begin(j);
-        const int jb = j & 1;
+        Batch nmeta = meta;
+        uint32_t nbits = 0;
+        if (j + 1 < pl.n_batches) { nmeta = pl.batches[j + 1]; nbits = my_bits[j + 1]; }
         if (meta.flags & 1) {
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s)
@@ -1010,9 +1061,8 @@ taf_tile_ws_kernel(TileParams tp) {
                     for (int k = 0; k < K / 2; ++k) v[s][p][k] = make_float2(kTafInit, kTafInit);
         }
         for (int b = 0; b < meta.nb; ++b) {
-            const uint32_t o0 = feed.s_off[jb * (kBatchBins + 1) + b], o1 = feed.s_off[jb * (kBatchBins + 1) + b + 1];
-            if (!feed.s_any[jb * kBatchBins + b]) continue;          // nobody saw an event: no ageing
-            if (o1 <= o0) {
+            if (!((bits >> (16 + b)) & 1u)) continue;               // nobody saw an event: no ageing
+            if (!((bits >> b) & 1u)) {
                 // the tile saw nothing in this bin, but some other tile did: everything ages
 #pragma unroll
                 for (int s = 0; s < SLOTS; ++s)
@@ -1022,7 +1072,7 @@ taf_tile_ws_kernel(TileParams tp) {
                         for (int k = 0; k < K / 2; ++k) v[s][p][k] = __fadd2_rn(v[s][p][k], minus1);
                 continue;
             }
-            named_sync(kBarFull0 + buf, kWsThreads);                 // the producers filled this accumulator
+            named_sync(kBarFull0 + buf, kHandOver);                  // the producers filled this accumulator
             uint2* my_acc = acc + buf * 2 * pl.P;
             uint4 a[SLOTS];
 #pragma unroll
@@ -1034,7 +1084,7 @@ taf_tile_ws_kernel(TileParams tp) {
                     if (a[s].x | a[s].z) *reinterpret_cast<uint4*>(my_acc + 2 * lp) = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
-            named_arrive(kBarEmpty0 + buf, kWsThreads);              // clean again: give it back
+            named_arrive(kBarEmpty0 + buf, kHandOver);               // clean again: give it back
             buf ^= 1;
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
@@ -1058,15 +1108,12 @@ taf_tile_ws_kernel(TileParams tp) {
                 }
             }
         }
-        bool published = false;
         if (meta.flags & 2) {
             const bool write_state = tp.emit_state || (j == pl.n_batches - 1);
-            float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
             if (tp.bulk_out) {
-                if (staged_once) {
-                    if (ctid < 2 * K) bulk_wait_read();              // previous window's rows have left smem
-                    named_sync(kBarConsumers, kConsumerThreads);
-                }
+                // stage the [2K][P] tile; the store warp sends it.  No consumer waits for another:
+                // each warp streams its columns, fences, signals and moves on to the next bin.
+                if (emitted > 0) named_sync(kBarStageFree, kStoreThreads + kConsumerThreads);
 #pragma unroll
                 for (int s = 0; s < SLOTS; ++s) {
                     const int lp = s * kConsumerThreads + ctid;
@@ -1080,15 +1127,10 @@ taf_tile_ws_kernel(TileParams tp) {
                         }
                 }
                 fence_async_smem();
-                feed.publish(j);                                     // next batch's offsets ride on the same barrier
-                named_sync(kBarConsumers, kConsumerThreads);
-                published = true;
-                if (ctid < 2 * K) {
-                    bulk_store_1d(o + (int64_t)ctid * HW, stage + ctid * pl.P, (uint32_t)npix * 4u);
-                    bulk_commit();
-                }
-                staged_once = true;
+                named_arrive(kBarStaged, kStoreThreads + kConsumerThreads);
+                ++emitted;
             } else {
+                float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
 #pragma unroll
                 for (int s = 0; s < SLOTS; ++s) {
                     const int lp = s * kConsumerThreads + ctid;
@@ -1116,9 +1158,9 @@ taf_tile_ws_kernel(TileParams tp) {
                 }
             }
         }
-        if (!published) feed.end(j);
+        meta = nmeta;
+        bits = nbits;
     }
-    if (tp.bulk_out && ctid < 2 * K) bulk_wait_all();               // smem must outlive the bulk reads
 }
 
 // ---- Event Volume over whole streams ----------------------------------------------------------
@@ -1289,7 +1331,7 @@ ev_tile_kernel(EvTileParams tp) {
 struct Layout {
     int P, n_tiles, slots;
     int64_t o_wbegin, o_wend, o_wstart, o_wnbins, o_wbinbase, o_batches, meta_bytes;
-    int64_t o_counts, o_binany, o_offrel, o_tiletotal, o_tilebase, o_origins, o_records, total;
+    int64_t o_counts, o_binany, o_offrel, o_tiletotal, o_tilebase, o_tilebits, o_origins, o_records, total;
     int n_batches_max;
 };
 
@@ -1323,6 +1365,7 @@ static int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W
     L.o_offrel = o;   o += align_up(4ll * L.n_tiles * (TB + 1), 16);
     L.o_tiletotal = o; o += align_up(4ll * L.n_tiles, 16);
     L.o_tilebase = o; o += align_up(4ll * (L.n_tiles + 1), 16);
+    L.o_tilebits = o; o += align_up(4ll * L.n_tiles * (n_batches > 0 ? n_batches : 1), 16);
     o = align_up(o, 256);
     L.o_origins = o;  o += align_up((int64_t)sizeof(ChunkOrigin) * (n_events / (kBucketThreads * kBucketPerThread) + 2), 256);
     L.o_records = o;  o += align_up(4ll * (n_events + 4ll * L.n_tiles), 256);
@@ -1445,6 +1488,7 @@ static int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* 
     pl.tile_total = reinterpret_cast<uint32_t*>(s + L.o_tiletotal);
     pl.tile_base = reinterpret_cast<uint32_t*>(s + L.o_tilebase);
     pl.records = reinterpret_cast<uint32_t*>(s + L.o_records);
+    pl.tile_bits = reinterpret_cast<uint32_t*>(s + L.o_tilebits);
     pl.n_windows = n_windows; pl.n_batches = (int)batches.size(); pl.TB = (int)TB;
     pl.n_tiles = L.n_tiles; pl.P = L.P; pl.H = H; pl.W = W;
     pl.div_abin = FastDiv::make((uint32_t)abin);
@@ -1479,12 +1523,14 @@ static int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* 
         EVREP_LAUNCH_CHECK();
         taf_scan_tiles_kernel<<<1, 1024, 0, st>>>(pl);
         EVREP_LAUNCH_CHECK();
+        taf_tile_bits_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
+        EVREP_LAUNCH_CHECK();
         if (grid > 0) {
             taf_bucket_kernel<true><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins, vec_ok);
             EVREP_LAUNCH_CHECK();
         }
     } else {
-        EVREP_CUDA(cudaMemsetAsync(s + L.o_tiletotal, 0, (size_t)(L.o_records - L.o_tiletotal), st));
+        EVREP_CUDA(cudaMemsetAsync(s + L.o_tiletotal, 0, (size_t)(L.o_origins - L.o_tiletotal), st));   // totals, bases, tile bits
     }
 
     return EVREP_OK;
@@ -1524,6 +1570,7 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
     TileParams tp;
     tp.pl = pl; tp.state = state_inout; tp.out = out; tp.out_stride = out_stride;
     tp.emit_state = emit_state_every_window;
+    tp.n_emits = n_windows;
     tp.span = (float)((double)abin + 1e-8);
     tp.bulk_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
 
