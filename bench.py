@@ -5,7 +5,7 @@ Workload (BASELINE.json configs[3]): one synthetic 1280
 recording per GPU, 10 s at 10 Mev/s = 100 M events (seed 1002 + rank), label every 50 ms
 from 100 ms (198 windows, 10 + 197 x 5 bins of 10 ms), Temporal Active Focus K=8 on the
 reference's 512x640 grid (gen4 coordinate policy), float32 [2K,H,W] tensor + state written
-per window.  A step = one pass over the whole recording: bucketing (5 kernels) + the
+per window.  A step = one pass over the whole recording: bucketing (6 kernels) + the
 persistent tile kernel.  Inputs (900 MB of SoA events) exceed the 126 MB L2.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -285,7 +285,7 @@ def main():
             "metric": "Mevents/s encoded (TAF K=8, 1MP)", "value": value, "unit": "Mevents/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": 6 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 7 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
             "windows": nw, "events_in_windows_per_gpu": n_in_windows,
         }))
     if world > 1:

@@ -168,3 +168,35 @@ def test_event_volume_stream_matches_oracle_and_single_window_path(K):
         e[:, 0] *= 0.5
         e[:, 1] *= 512 / 720
         assert close(got[i], oe.event_volume(e, (512, 640), K)), i
+
+
+def test_single_role_kernel_equals_warp_specialised(monkeypatch):
+    """The non-specialised tile kernel (fallback when the staging tile does not fit next to two
+    accumulator buffers) gives bit-identical results."""
+    t, x, y, p = synth.make_stream(720, 1280, 150000, 8e6, 31)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    maps = ops.make_coord_maps((720, 1280), (512, 640), DEV)
+    windows = [(0, idx(t, 80000), 0, 8, 1), (idx(t, 80000), idx(t, 150000), 80000, 7, 0)]
+    outs = []
+    for mode in ("ws", "single"):
+        monkeypatch.setenv("EVREP_TAF_TILE_KERNEL", mode)
+        state = ops.taf_fresh_state((512, 640), 8, DEV)
+        outs.append((ops.taf_stream(ev, windows, 10000, (512, 640), 8, state, maps).clone(), state))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_stream_argument_errors():
+    from frlw_evd_b200 import _lib
+    t, x, y, p = synth.make_stream(240, 304, 20000, 1e6, 3)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    state = ops.taf_fresh_state((240, 304), 8, DEV)
+    w = [(0, ev.n, 0, 2, 1)]
+    with pytest.raises(_lib.EvrepError, match="invalid argument"):
+        ops.taf_stream(ev, w, 10000, (240, 304), 5, ops.taf_fresh_state((240, 304), 5, DEV))      # K must be 4 or 8
+    with pytest.raises(_lib.EvrepError, match="out of range"):
+        ops.taf_stream(ev, w, 300000, (240, 304), 8, state)                                        # abin > 18 bits
+    with pytest.raises(_lib.EvrepError, match="invalid argument"):
+        ops.taf_stream(ev, [(0, ev.n, 0, 2, 1), (10, ev.n, 0, 2, 0)], 10000, (240, 304), 8, state)  # overlapping windows
+    with pytest.raises(_lib.EvrepError, match="out of range"):
+        ops.event_volume_stream(ev, [(0, ev.n, 0)], 300000, (240, 304), 5)
+    assert ops.taf_stream(ev, [], 10000, (240, 304), 8, state).shape[0] == 0                       # no windows: no-op
