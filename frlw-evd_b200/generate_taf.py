@@ -175,23 +175,41 @@ class HostPipeline:
         return out_host
 
 
+def encode_recording_to_files(rec: DeviceRecording, labels, name: str, mode: str, target_dir: str, geom: Geometry,
+                              writer, volume_bins=VOLUME_BINS, abin=ABIN) -> int:
+    """Host pipeline + file layout of ``generate_taf.py:226-235``: pinned ``.dat`` payload in,
+    ``taf/<mode>/bins{K/2}`` and ``bins{K}`` files out.  Returns the number of windows."""
+    plan = plan_windows(rec.loader, labels, abin, volume_bins)
+    if not plan:
+        return 0
+    pipe = HostPipeline(geom, plan, volume_bins, abin)
+    out = torch.empty(pipe.out_shape, dtype=torch.uint8, pin_memory=True)
+    pipe.run(rec.raw_pinned, out)
+    torch.cuda.synchronize()
+    half = volume_bins // 2
+    host = out.numpy()
+    for i, w in enumerate(plan):
+        fname = name + "_" + str(w.label) + ".npy"
+        writer.put(host[i, :half], target_dir, "taf", mode, "bins{0}".format(half), fname)
+        writer.put(host[i, half:], target_dir, "taf", mode, "bins{0}".format(volume_bins), fname)
+    writer.drain()                       # `out` is released when this returns
+    return len(plan)
+
+
 def main(argv=None):
+    from .recordings import AsyncWriter
     args = parse_args("gen4", argv)
     geom = Geometry.for_dataset(args.dataset)
-    half = VOLUME_BINS // 2
+    writer = AsyncWriter()
     total_time, total_count = 0.0, 0
     for mode, name, event_file, labels in iter_recordings(args.raw_dir, args.label_dir):
-        rec = DeviceRecording(event_file)
-        plan = plan_windows(rec.loader, labels)
-        torch.cuda.synchronize()
+        rec = DeviceRecording(event_file, decode=False)
         tick = time.time()
-        for label, u8 in encode_recording(rec, plan, geom):
-            fname = name + "_" + str(label) + ".npy"
-            dump_u8(u8[:half], args.target_dir, "taf", mode, "bins{0}".format(half), fname)
-            dump_u8(u8[half:], args.target_dir, "taf", mode, "bins{0}".format(VOLUME_BINS), fname)
+        n = encode_recording_to_files(rec, labels, name, mode, args.target_dir, geom, writer)
         if mode == "test":
             total_time += time.time() - tick
-            total_count += len(plan)
+            total_count += n
+    writer.close()
     if total_count:
         print("Average Representation time: ", total_time / total_count)
 

@@ -79,6 +79,13 @@ def encode_one(rep: str, dataset: str, mode: str, name: str, event_file: str, la
 
     geom = Geometry.for_dataset(dataset)
     labels = npy_events_tools.read_label_times(label_file)
+    if rep == "taf":                      # host pipeline: H2D, kernels and D2H overlap, files written by a thread pool
+        from .recordings import AsyncWriter
+        rec = DeviceRecording(event_file, decode=False)
+        writer = AsyncWriter()
+        windows = taf.encode_recording_to_files(rec, labels, name, mode, target_dir, geom, writer)
+        writer.close()
+        return {"events": rec.n_events, "windows": windows, "bytes_written": writer.bytes_written}
     rec = DeviceRecording(event_file)
     windows = written = 0
 
@@ -87,14 +94,7 @@ def encode_one(rep: str, dataset: str, mode: str, name: str, event_file: str, la
         dump_u8(u8, *path)
         written += u8.numel()
 
-    if rep == "taf":
-        half = taf.VOLUME_BINS // 2
-        for label, u8 in taf.encode_recording(rec, taf.plan_windows(rec.loader, labels), geom):
-            fname = name + "_" + str(label) + ".npy"
-            put(u8[:half], target_dir, "taf", mode, "bins{0}".format(half), fname)
-            put(u8[half:], target_dir, "taf", mode, "bins{0}".format(taf.VOLUME_BINS), fname)
-            windows += 1
-    elif rep == "count_image":
+    if rep == "count_image":
         sizes = eci.windows_for(dataset)
         for label, frames in eci.encode_recording(rec, labels, geom, sizes):
             for n, u8 in zip(sizes, frames):

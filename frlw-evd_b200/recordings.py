@@ -78,17 +78,50 @@ def iter_recordings(raw_dir, label_dir):
 
 
 class DeviceRecording:
-    """A recording resident on the GPU: raw payload copied once, decoded by the CUDA
-    decoder into SoA buffers; the memory-mapped loader answers the seek queries."""
+    """A recording staged for the GPU: the raw payload sits in pinned host memory
+    (``raw_pinned``); with ``decode=True`` it is also copied to the device and decoded by the
+    CUDA decoder into SoA buffers (``events``).  The memory-mapped loader answers the seek
+    queries."""
 
-    def __init__(self, path: str, device="cuda"):
+    def __init__(self, path: str, device="cuda", decode=True):
         self.loader = PSEELoader(path)
         payload = self.loader.raw_bytes()
-        staged = torch.empty(payload.shape[0], dtype=torch.uint8, pin_memory=payload.shape[0] > 0)
-        np.copyto(staged.numpy(), payload)               # file (page cache) -> pinned host memory, once
-        self.events = ops.decode_dat(staged.to(device, non_blocking=True))
+        self.raw_pinned = torch.empty(payload.shape[0], dtype=torch.uint8, pin_memory=payload.shape[0] > 0)
+        np.copyto(self.raw_pinned.numpy(), payload)      # file (page cache) -> pinned host memory, once
+        self.n_events = payload.shape[0] // 8
+        self.events = ops.decode_dat(self.raw_pinned.to(device, non_blocking=True)) if decode else None
 
 
 def dump_u8(tensor_u8: torch.Tensor, *path) -> None:
     os.makedirs(os.path.join(*path[:-1]), exist_ok=True)
     tensor_u8.cpu().numpy().tofile(os.path.join(*path))
+
+
+class AsyncWriter:
+    """Writes raw uint8 arrays to files on a small thread pool (``ndarray.tofile`` releases
+    the GIL), so the file system works while the GPU encodes the next recording."""
+
+    def __init__(self, workers: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=workers)
+        self._pending = []
+        self._dirs = set()
+        self.bytes_written = 0
+
+    def put(self, array: np.ndarray, *path) -> None:
+        folder = os.path.join(*path[:-1])
+        if folder not in self._dirs:
+            os.makedirs(folder, exist_ok=True)
+            self._dirs.add(folder)
+        self.bytes_written += array.nbytes
+        self._pending.append(self._pool.submit(array.tofile, os.path.join(*path)))
+
+    def drain(self) -> None:
+        """Block until everything submitted so far is on disk (buffers may then be reused)."""
+        for f in self._pending:
+            f.result()
+        self._pending = []
+
+    def close(self) -> None:
+        self.drain()
+        self._pool.shutdown()
