@@ -1,0 +1,560 @@
+// Bucketing passes of the whole-stream encoders: a counting sort of the time-ordered events
+// by (sensor tile, bin) into packed 4-byte records  [ d:18 | local pixel:13 | p:1 ],
+// d = t - bin start.  Count (shared-memory histograms per 4096-event chunk), scan (per tile
+// row, then across tiles), scatter (records ordered in shared memory, runs written with
+// consecutive addresses).  Also the host-side front end shared by the stream entry points.
+#include "stream_common.cuh"
+
+namespace evrep {
+
+// Window descriptor staged in shared memory by the bucketing kernels.
+struct WinInfo {
+    int64_t begin, end, start;
+    int nbins, binbase;
+};
+
+__device__ __forceinline__ WinInfo load_window(const StreamPlan& pl, int w) {
+    WinInfo wi;
+    wi.begin = pl.w_begin[w]; wi.end = pl.w_end[w]; wi.start = pl.w_start[w];
+    wi.nbins = pl.w_nbins[w]; wi.binbase = pl.w_binbase[w];
+    return wi;
+}
+
+// First window whose event range ends after event index i.
+__device__ __forceinline__ int first_window(const StreamPlan& pl, int64_t i) {
+    int lo = 0, hi = pl.n_windows;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(pl.w_end + mid) > i) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// Bin of a timestamp inside window `wi` and the offset d from the bin start:
+// z = clamp(floor((t - start) / abin), 0, nbins - 1) -- inclusive edges, later bin wins
+// (generate_taf.py:201-202) -- and d = t - (start + z abin), saturated to 18 bits.
+__device__ __forceinline__ void bin_of(const StreamPlan& pl, const WinInfo& wi, uint32_t t, uint32_t& z, uint32_t& d) {
+    const int64_t dt = (int64_t)t - wi.start;
+    z = 0; d = 0;
+    if (dt > 0) {
+        const uint32_t u = dt > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)dt;
+        z = pl.div_abin.div(u);
+        if (z > (uint32_t)(wi.nbins - 1)) z = wi.nbins - 1;
+        const uint32_t rem = u - z * pl.abin;
+        d = rem > kDMax ? kDMax : rem;
+    }
+}
+
+// Block-wide exclusive scan of n <= kBucketThreads * 16 shared-memory counters.
+// Returns the total.  `tmp` holds one word per warp (+1).
+__device__ __forceinline__ uint32_t block_exclusive_scan(const uint32_t* in, uint32_t* out, int n, uint32_t* tmp) {
+    const int per = (n + kBucketThreads - 1) / kBucketThreads;
+    const int lo = threadIdx.x * per, hi = min(lo + per, n);
+    uint32_t mine = 0;
+    for (int i = lo; i < hi; ++i) mine += in[i];
+    uint32_t incl = mine;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) tmp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < kBucketThreads / 32 ? tmp[lane] : 0u, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        if (lane < kBucketThreads / 32) tmp[lane] = wi - w;
+        if (lane == kBucketThreads / 32 - 1) tmp[kBucketThreads / 32] = wi;
+    }
+    __syncthreads();
+    uint32_t run = tmp[wid] + incl - mine;
+    for (int i = lo; i < hi; ++i) { const uint32_t c = in[i]; out[i] = run; run += c; }
+    const uint32_t total = tmp[kBucketThreads / 32];
+    __syncthreads();                     // `out` is complete (and `tmp` reusable) for every thread
+    return total;
+}
+
+// Per-chunk prologue of the bucketing passes, computed once by a tiny kernel: the window of
+// the chunk's first event, the first global bin the chunk can touch and whether the whole
+// chunk lies inside that window (the fast path).
+struct ChunkOrigin {
+    WinInfo win;
+    int w0, gb0, single, pad;
+};
+
+__global__ void __launch_bounds__(256)
+taf_chunk_origin_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, ChunkOrigin* __restrict__ origins) {
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= n_chunks) return;
+    const int64_t c0 = ev_first + (int64_t)chunk * (kBucketThreads * kBucketPerThread);
+    const int64_t c1 = min(c0 + kBucketThreads * kBucketPerThread, ev_last);
+    ChunkOrigin o;
+    o.w0 = first_window(pl, c0);
+    o.gb0 = 0; o.single = 0; o.pad = 0;
+    o.win.begin = o.win.end = o.win.start = 0; o.win.nbins = 0; o.win.binbase = 0;
+    if (o.w0 < pl.n_windows) {
+        const WinInfo wi = load_window(pl, o.w0);
+        o.win = wi;
+        o.single = (c0 >= wi.begin && c1 <= wi.end && wi.nbins > 0) ? 1 : 0;
+        const int64_t i = c0 > wi.begin ? c0 : wi.begin;
+        o.gb0 = wi.binbase;
+        if (i < c1 && i < wi.end && wi.nbins > 0) {
+            uint32_t z, d;
+            bin_of(pl, wi, ev.t[i], z, d);
+            o.gb0 += (int)z;
+        }
+    }
+    origins[chunk] = o;
+}
+
+// Shared-memory carve-up of the bucketing kernels.
+struct BucketSmem {
+    int lutx, luty, hist, loff, gbase, sorted, skey, total;
+    __host__ __device__ BucketSmem(int lut_w, int lut_h, int nh, bool scatter) {
+        int o = 0;
+        lutx = o;  o += (lut_w * 2 + 15) / 16 * 16;
+        luty = o;  o += (lut_h * 2 + 15) / 16 * 16;
+        hist = o;  o += nh * 4;
+        loff = o;  o += scatter ? nh * 4 : 0;
+        gbase = o; o += scatter ? nh * 4 : 0;
+        sorted = o; o += scatter ? kBucketThreads * kBucketPerThread * 4 : 0;
+        skey = o;  o += scatter ? kBucketThreads * kBucketPerThread * 2 : 0;
+        total = (o + 15) / 16 * 16;
+    }
+};
+
+// Bucketing passes.  Persistent CTAs walk 4096-event chunks of the time-ordered stream.
+//  count   (kScatter = false): per-chunk shared-memory histogram over (local bin, tile),
+//          flushed with one global atomic per non-empty counter; sets the per-bin flags.
+//  scatter (kScatter = true):  the same histogram with ranks, a block scan, one global
+//          reservation per non-empty counter, then the chunk's records are ordered in shared
+//          memory so that each (tile, bin) run is written with consecutive addresses.
+template <bool kScatter>
+__global__ void __launch_bounds__(kBucketThreads, 2)
+taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, int lut_w, int lut_h,
+                  const ChunkOrigin* __restrict__ origins, int vec_ok) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    const int nh = kLocalBins * pl.n_tiles;
+    const bool use_lut = ev.xmap != nullptr && ev.ymap != nullptr;
+    const BucketSmem lay(use_lut ? lut_w : 0, use_lut ? lut_h : 0, nh, kScatter);
+    uint16_t* s_lutx = reinterpret_cast<uint16_t*>(bsm + lay.lutx);
+    uint16_t* s_luty = reinterpret_cast<uint16_t*>(bsm + lay.luty);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(bsm + lay.hist);
+    uint32_t* loff = reinterpret_cast<uint32_t*>(bsm + lay.loff);
+    uint32_t* gbase = reinterpret_cast<uint32_t*>(bsm + lay.gbase);
+    uint32_t* sorted = reinterpret_cast<uint32_t*>(bsm + lay.sorted);
+    uint16_t* skey = reinterpret_cast<uint16_t*>(bsm + lay.skey);
+    __shared__ uint32_t s_tmp[kBucketThreads / 32 + 1];
+
+    if (use_lut) {
+        for (int i = threadIdx.x; i < lut_w; i += kBucketThreads) s_lutx[i] = ev.xmap[i];
+        for (int i = threadIdx.x; i < lut_h; i += kBucketThreads) s_luty[i] = ev.ymap[i];
+    }
+    const uint32_t W = pl.W, H = pl.H;
+
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t c0 = ev_first + (int64_t)chunk * (kBucketThreads * kBucketPerThread);
+        const int64_t c1 = min(c0 + kBucketThreads * kBucketPerThread, ev_last);
+        const ChunkOrigin org = origins[chunk];            // same address for every thread: one broadcast load
+        __syncthreads();                                   // previous chunk is done with smem
+        for (int i = threadIdx.x; i < nh; i += kBucketThreads) hist[i] = 0;
+        const int gb0 = org.gb0;
+        const bool single = org.single != 0;
+        int w = org.w0;
+        WinInfo wi = org.win;
+
+        // all global loads of the chunk are issued before any of them is used
+        const bool fast = single && (c1 - c0) == kBucketThreads * kBucketPerThread &&
+                          wi.start >= 0 && wi.start <= 0xFFFFFFFFll;
+        // per event: timestamp and x | y << 14 | p << 28 (the .dat word), kBad when out of range
+        constexpr uint32_t kBad = 0xFFFFFFFFu;
+        auto pack = [](uint32_t x, uint32_t y, uint32_t p) -> uint32_t {
+            return (((x | y) >> 14) | (p >> 1)) ? kBad : (x | (y << 14) | (p << 28));
+        };
+        uint32_t tt[kBucketPerThread], xyp[kBucketPerThread];
+        if (fast && vec_ok) {
+            // 4 consecutive events per 128/64/64/32-bit load (c0 is a multiple of 4 events)
+            static_assert(kBucketPerThread % 4 == 0, "vector path loads events in groups of 4");
+#pragma unroll
+            for (int g = 0; g < kBucketPerThread / 4; ++g) {
+                const int64_t base = c0 + ((int64_t)g * kBucketThreads + threadIdx.x) * 4;
+                const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(ev.t + base));
+                const uint2 x4 = __ldg(reinterpret_cast<const uint2*>(ev.x + base));
+                const uint2 y4 = __ldg(reinterpret_cast<const uint2*>(ev.y + base));
+                const uint32_t p4 = __ldg(reinterpret_cast<const uint32_t*>(ev.p + base));
+                tt[4 * g + 0] = t4.x; tt[4 * g + 1] = t4.y; tt[4 * g + 2] = t4.z; tt[4 * g + 3] = t4.w;
+                xyp[4 * g + 0] = pack(x4.x & 0xFFFFu, y4.x & 0xFFFFu, p4 & 0xFFu);
+                xyp[4 * g + 1] = pack(x4.x >> 16, y4.x >> 16, (p4 >> 8) & 0xFFu);
+                xyp[4 * g + 2] = pack(x4.y & 0xFFFFu, y4.y & 0xFFFFu, (p4 >> 16) & 0xFFu);
+                xyp[4 * g + 3] = pack(x4.y >> 16, y4.y >> 16, p4 >> 24);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kBucketPerThread; ++k) {
+                const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
+                xyp[k] = kBad;
+                if (i < c1) { tt[k] = __ldg(ev.t + i); xyp[k] = pack(__ldg(ev.x + i), __ldg(ev.y + i), __ldg(ev.p + i)); }
+            }
+        }
+
+        __syncthreads();                                   // histogram is zeroed
+        // per event: (smem counter << 12) | rank inside the chunk, or kNone when dropped
+        constexpr uint32_t kNone = 0xFFFFFFFFu;
+        uint32_t slot[kBucketPerThread], rec[kBucketPerThread] = {};
+
+        // count / rank one classified event
+        auto deposit = [&](int k, uint32_t tile, int gbin) {
+            const uint32_t lb = (uint32_t)(gbin - gb0);
+            if (lb < (uint32_t)kLocalBins) {
+                const uint32_t key = lb * (uint32_t)pl.n_tiles + tile;
+                if (kScatter) slot[k] = (key << 12) | atomicAdd(&hist[key], 1u);
+                else atomicAdd(&hist[key], 1u);
+            } else {                          // unsorted input or a very sparse stream: go straight to global
+                uint32_t* cursor = pl.counts + (int64_t)tile * pl.TB + gbin;
+                if (kScatter)
+                    pl.records[pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] + atomicAdd(cursor, 1u)] = rec[k];
+                else { atomicAdd(cursor, 1u); pl.bin_any[gbin] = 1u; }
+            }
+        };
+        // map raw coordinates to the grid; false when the event is to be dropped
+        auto locate = [&](int k, uint32_t& pix) -> bool {
+            uint32_t xm = xyp[k] & 0x3FFFu, ym = (xyp[k] >> 14) & 0x3FFFu;
+            bool ok = xyp[k] != kBad;
+            if (use_lut) {
+                ok = ok && xm < (uint32_t)lut_w && ym < (uint32_t)lut_h;
+                xm = s_lutx[min(xm, (uint32_t)lut_w - 1u)];
+                ym = s_luty[min(ym, (uint32_t)lut_h - 1u)];
+            }
+            pix = ym * W + xm;
+            return ok && xm < W && ym < H;
+        };
+
+        if (fast) {
+            // the whole chunk lies in one window: 32-bit time arithmetic, no bounds checks
+            const uint32_t start32 = (uint32_t)wi.start, zmax = (uint32_t)(wi.nbins - 1);
+#pragma unroll
+            for (int k = 0; k < kBucketPerThread; ++k) {
+                slot[k] = kNone;
+                uint32_t pix;
+                if (!locate(k, pix)) continue;
+                const uint32_t u = tt[k] >= start32 ? tt[k] - start32 : 0u;
+                const uint32_t z = min(pl.div_abin.div(u), zmax);
+                const uint32_t tile = pl.div_P.div(pix);
+                if (kScatter) rec[k] = (min(u - z * pl.abin, kDMax) << 14) | ((pix - tile * pl.P) << 1) | (xyp[k] >> 28);
+                deposit(k, tile, wi.binbase + (int)z);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kBucketPerThread; ++k) {
+                const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
+                slot[k] = kNone;
+                if (i >= c1) continue;
+                if (!single) {                  // chunk straddles a window boundary or a gap
+                    while (w < pl.n_windows && i >= __ldg(pl.w_end + w)) ++w;
+                    if (w >= pl.n_windows) continue;
+                    wi = load_window(pl, w);
+                    if (i < wi.begin || wi.nbins <= 0) continue;
+                }
+                uint32_t pix;
+                if (!locate(k, pix)) continue;
+                uint32_t z, d;
+                bin_of(pl, wi, tt[k], z, d);
+                const uint32_t tile = pl.div_P.div(pix);
+                rec[k] = (d << 14) | ((pix - tile * pl.P) << 1) | (xyp[k] >> 28);
+                deposit(k, tile, wi.binbase + (int)z);
+            }
+        }
+        __syncthreads();
+        if (!kScatter) {
+            for (int i = threadIdx.x; i < nh; i += kBucketThreads) {
+                const uint32_t c = hist[i];
+                if (!c) continue;
+                const int lb = i / pl.n_tiles, tile = i - lb * pl.n_tiles, gbin = gb0 + lb;
+                atomicAdd(pl.counts + (int64_t)tile * pl.TB + gbin, c);
+                pl.bin_any[gbin] = 1u;
+            }
+            continue;
+        }
+        const uint32_t n_valid = block_exclusive_scan(hist, loff, nh, s_tmp);
+        for (int i = threadIdx.x; i < nh; i += kBucketThreads) {
+            const uint32_t c = hist[i];
+            if (!c) continue;
+            const int lb = i / pl.n_tiles, tile = i - lb * pl.n_tiles, gbin = gb0 + lb;
+            gbase[i] = pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] +
+                       atomicAdd(pl.counts + (int64_t)tile * pl.TB + gbin, c) - loff[i];
+        }
+#pragma unroll
+        for (int k = 0; k < kBucketPerThread; ++k) {
+            if (slot[k] == kNone) continue;
+            const uint32_t key = slot[k] >> 12;
+            const uint32_t pos = loff[key] + (slot[k] & 0xFFFu);
+            sorted[pos] = rec[k];
+            skey[pos] = (uint16_t)key;
+        }
+        __syncthreads();
+        for (uint32_t pos = threadIdx.x; pos < n_valid; pos += kBucketThreads)
+            pl.records[gbase[skey[pos]] + pos] = sorted[pos];
+    }
+}
+
+// Exclusive scan of one tile's per-bin counts -> relative offsets; counts are zeroed so
+// that the scatter pass can reuse them as cursors.
+__global__ void __launch_bounds__(256)
+taf_scan_rows_kernel(StreamPlan pl) {
+    __shared__ uint32_t warp_sum[8];
+    __shared__ uint32_t s_carry;
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* cnt = pl.counts + (int64_t)tile * pl.TB;
+    uint32_t* off = pl.off_rel + (int64_t)tile * (pl.TB + 1);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < pl.TB; base += 256 * 4) {
+        const int i0 = base + threadIdx.x * 4;
+        uint32_t c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = (i0 + k < pl.TB) ? cnt[i0 + k] : 0u;
+        const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        uint32_t before = s_carry;
+        for (int k = 0; k < wid; ++k) before += warp_sum[k];
+        uint32_t run = before + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < pl.TB) { off[i0 + k] = run; cnt[i0 + k] = 0u; }
+            run += c[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { off[pl.TB] = s_carry; pl.tile_total[tile] = s_carry; }
+}
+
+__global__ void __launch_bounds__(1024)
+taf_scan_tiles_kernel(StreamPlan pl) {         // n_tiles <= kMaxTiles = 2 * 1024
+    __shared__ uint32_t warp_sum[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t c[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = threadIdx.x * 2 + k;
+        c[k] = i < pl.n_tiles ? ((pl.tile_total[i] + 3u) & ~3u) : 0u;
+    }
+    const uint32_t mine = c[0] + c[1];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int k = 0; k < wid; ++k) before += warp_sum[k];
+    uint32_t run = before + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = threadIdx.x * 2 + k;
+        if (i < pl.n_tiles) pl.tile_base[i] = run;
+        run += c[k];
+        if (i == pl.n_tiles - 1) pl.tile_base[pl.n_tiles] = run;
+    }
+}
+
+// Per (tile, batch) summary for the consumer warps of the tile kernel: which bins of the batch
+// have records of this tile (bit b) and which are non-empty anywhere (bit 16 + b).
+static_assert(kBatchBins <= 16, "two 16-bit masks per batch");
+__global__ void __launch_bounds__(256)
+taf_tile_bits_kernel(StreamPlan pl) {
+    const int tile = blockIdx.x;
+    const uint32_t* off = pl.off_rel + (int64_t)tile * (pl.TB + 1);
+    for (int j = threadIdx.x; j < pl.n_batches; j += blockDim.x) {
+        const Batch m = pl.batches[j];
+        uint32_t bits = 0;
+        for (int b = 0; b < m.nb; ++b) {
+            if (off[m.gbin0 + b + 1] > off[m.gbin0 + b]) bits |= 1u << b;
+            if (pl.bin_any[m.gbin0 + b]) bits |= 1u << (16 + b);
+        }
+        pl.tile_bits[(int64_t)tile * pl.n_batches + j] = bits;
+    }
+}
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n_batches, Layout& L, int tiles_per_sm) {
+    const int64_t HW = (int64_t)H * W;
+    const int sms = sm_count() * tiles_per_sm;
+    int64_t P = (HW + sms - 1) / sms;
+    P = (P + 31) / 32 * 32;
+    if (P > kTafThreads * kMaxSlots) P = kTafThreads * kMaxSlots;
+    if (P < 32) P = 32;
+    L.P = (int)P;
+    L.n_tiles = (int)((HW + P - 1) / P);
+    L.slots = (int)((P + kTafThreads - 1) / kTafThreads);
+    if (L.n_tiles > kMaxTiles) return EVREP_ERR_RANGE;
+    if (n_events >= (1ll << 31) || TB >= (1ll << 24) || (int64_t)L.n_tiles * (TB + 1) >= (1ll << 31)) return EVREP_ERR_RANGE;
+    L.n_batches_max = n_batches;
+    int64_t o = 0;
+    L.o_wbegin = o;   o += align_up(8ll * n_windows, 16);
+    L.o_wend = o;     o += align_up(8ll * n_windows, 16);
+    L.o_wstart = o;   o += align_up(8ll * n_windows, 16);
+    L.o_wnbins = o;   o += align_up(4ll * n_windows, 16);
+    L.o_wbinbase = o; o += align_up(4ll * (n_windows + 1), 16);
+    L.o_batches = o;  o += align_up(16ll * n_batches, 16);
+    L.meta_bytes = o;
+    o = align_up(o, 256);
+    L.o_counts = o;   o += align_up(4ll * L.n_tiles * TB, 16);
+    L.o_binany = o;   o += align_up(4ll * TB, 16);
+    L.o_offrel = o;   o += align_up(4ll * L.n_tiles * (TB + 1), 16);
+    L.o_tiletotal = o; o += align_up(4ll * L.n_tiles, 16);
+    L.o_tilebase = o; o += align_up(4ll * (L.n_tiles + 1), 16);
+    L.o_tilebits = o; o += align_up(4ll * L.n_tiles * (n_batches > 0 ? n_batches : 1), 16);
+    o = align_up(o, 256);
+    L.o_origins = o;  o += align_up((int64_t)sizeof(ChunkOrigin) * (n_events / (kBucketThreads * kBucketPerThread) + 2), 256);
+    L.o_records = o;  o += align_up(4ll * (n_events + 4ll * L.n_tiles), 256);
+    L.total = o;
+    return EVREP_OK;
+}
+
+int64_t batches_upper_bound(int n_windows, int64_t TB) {
+    return (int64_t)n_windows + TB / kBatchBins + 1;
+}
+
+// Shared front end of the stream entry points: validates the window list, uploads the
+// window / batch tables and runs the bucketing passes.  On return `pl` describes the bucketed
+// records of every (tile, bin).
+int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+                          const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W,
+                          const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                          void* scratch, int64_t scratch_bytes, cudaStream_t st, StreamPlan& pl, Layout& L,
+                   int tiles_per_sm) {
+    if (xmap && ymap && (sensor_h <= 0 || sensor_w <= 0 || sensor_h > EVREP_COORD_LUT_LEN || sensor_w > EVREP_COORD_LUT_LEN))
+        return EVREP_ERR_ARG;
+    if ((uint32_t)abin > kDMax) return EVREP_ERR_RANGE;
+    if (!windows_host || (n_events > 0 && (!t || !x || !y || !p))) return EVREP_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(scratch) & 255) return EVREP_ERR_ARG;
+
+    // windows -> bins -> batches (host, O(n_windows + bins / 16))
+    int64_t TB = 0;
+    int64_t prev_end = 0;
+    for (int w = 0; w < n_windows; ++w) {
+        const evrep_taf_window& win = windows_host[w];
+        if (win.ev_begin < prev_end || win.ev_end < win.ev_begin || win.ev_end > n_events || win.n_bins < 0) return EVREP_ERR_ARG;
+        if ((int64_t)win.n_bins * abin >= (1ll << 32)) return EVREP_ERR_RANGE;
+        prev_end = win.ev_end;
+        TB += win.n_bins;
+    }
+    std::vector<Batch> batches;
+    batches.reserve((size_t)batches_upper_bound(n_windows, TB));
+    {
+        int gbin = 0;
+        for (int w = 0; w < n_windows; ++w) {
+            const int nb = windows_host[w].n_bins;
+            int done = 0;
+            do {
+                Batch b;
+                b.gbin0 = gbin + done;
+                b.nb = nb - done < kBatchBins ? nb - done : kBatchBins;
+                b.flags = (done == 0 && windows_host[w].fresh ? 1 : 0) | (done + b.nb >= nb ? 2 : 0);
+                b.win = w;
+                batches.push_back(b);
+                done += b.nb;
+            } while (done < nb);
+            gbin += nb;
+        }
+    }
+    int rc = make_layout(n_events, n_windows, TB, H, W, (int)batches.size(), L, tiles_per_sm);
+    if (rc) return rc;
+    if (scratch_bytes < L.total) return EVREP_ERR_SCRATCH;
+    // pack and upload the metadata
+    std::vector<unsigned char> meta((size_t)L.meta_bytes, 0);
+    int64_t* hb = reinterpret_cast<int64_t*>(meta.data() + L.o_wbegin);
+    int64_t* he = reinterpret_cast<int64_t*>(meta.data() + L.o_wend);
+    int64_t* hs = reinterpret_cast<int64_t*>(meta.data() + L.o_wstart);
+    int32_t* hn = reinterpret_cast<int32_t*>(meta.data() + L.o_wnbins);
+    int32_t* hbb = reinterpret_cast<int32_t*>(meta.data() + L.o_wbinbase);
+    int32_t base = 0;
+    for (int w = 0; w < n_windows; ++w) {
+        hb[w] = windows_host[w].ev_begin; he[w] = windows_host[w].ev_end; hs[w] = windows_host[w].start_time;
+        hn[w] = windows_host[w].n_bins; hbb[w] = base;
+        base += windows_host[w].n_bins;
+    }
+    hbb[n_windows] = base;
+    memcpy(meta.data() + L.o_batches, batches.data(), batches.size() * sizeof(Batch));
+    char* s = reinterpret_cast<char*>(scratch);
+    EVREP_CUDA(cudaMemcpyAsync(s, meta.data(), (size_t)L.meta_bytes, cudaMemcpyHostToDevice, st));
+    // pageable source: the copy has been staged when the call returns, `meta` may die
+
+    pl.w_begin = reinterpret_cast<const int64_t*>(s + L.o_wbegin);
+    pl.w_end = reinterpret_cast<const int64_t*>(s + L.o_wend);
+    pl.w_start = reinterpret_cast<const int64_t*>(s + L.o_wstart);
+    pl.w_nbins = reinterpret_cast<const int32_t*>(s + L.o_wnbins);
+    pl.w_binbase = reinterpret_cast<const int32_t*>(s + L.o_wbinbase);
+    pl.batches = reinterpret_cast<const Batch*>(s + L.o_batches);
+    pl.counts = reinterpret_cast<uint32_t*>(s + L.o_counts);
+    pl.bin_any = reinterpret_cast<uint32_t*>(s + L.o_binany);
+    pl.off_rel = reinterpret_cast<uint32_t*>(s + L.o_offrel);
+    pl.tile_total = reinterpret_cast<uint32_t*>(s + L.o_tiletotal);
+    pl.tile_base = reinterpret_cast<uint32_t*>(s + L.o_tilebase);
+    pl.records = reinterpret_cast<uint32_t*>(s + L.o_records);
+    pl.tile_bits = reinterpret_cast<uint32_t*>(s + L.o_tilebits);
+    pl.n_windows = n_windows; pl.n_batches = (int)batches.size(); pl.TB = (int)TB;
+    pl.n_tiles = L.n_tiles; pl.P = L.P; pl.H = H; pl.W = W;
+    pl.div_abin = FastDiv::make((uint32_t)abin);
+    pl.div_P = FastDiv::make((uint32_t)L.P);
+    pl.abin = (uint32_t)abin;
+
+    if (TB > 0) {
+        EVREP_CUDA(cudaMemsetAsync(s + L.o_counts, 0, (size_t)(L.o_offrel - L.o_counts), st));   // counts + bin_any
+        // chunks start on a multiple of 4 events so that full chunks can use vector loads
+        const int64_t ev_first = windows_host[0].ev_begin & ~3ll, ev_last = windows_host[n_windows - 1].ev_end;
+        const int vec_ok = !((reinterpret_cast<uintptr_t>(t) & 15) | (reinterpret_cast<uintptr_t>(x) & 7) |
+                             (reinterpret_cast<uintptr_t>(y) & 7) | (reinterpret_cast<uintptr_t>(p) & 3));
+        const int64_t per_cta = kBucketThreads * kBucketPerThread;
+        const int64_t n_chunks = (ev_last - ev_first + per_cta - 1) / per_cta;
+        if (n_chunks >= (1ll << 31)) return EVREP_ERR_RANGE;
+        const int grid = (int)(n_chunks < 2ll * sm_count() ? n_chunks : 2ll * sm_count());
+        const bool use_lut = xmap && ymap;
+        const int nh = kLocalBins * L.n_tiles;
+        const size_t smem_count = (size_t)BucketSmem(use_lut ? sensor_w : 0, use_lut ? sensor_h : 0, nh, false).total;
+        const size_t smem_scatter = (size_t)BucketSmem(use_lut ? sensor_w : 0, use_lut ? sensor_h : 0, nh, true).total;
+        EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+        EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+        SoA ev{t, x, y, p, xmap, ymap};
+        ChunkOrigin* origins = reinterpret_cast<ChunkOrigin*>(s + L.o_origins);
+        if (grid > 0) {
+            taf_chunk_origin_kernel<<<(int)((n_chunks + 255) / 256), 256, 0, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, origins);
+            EVREP_LAUNCH_CHECK();
+            taf_bucket_kernel<false><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins, vec_ok);
+            EVREP_LAUNCH_CHECK();
+        }
+        taf_scan_rows_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
+        EVREP_LAUNCH_CHECK();
+        taf_scan_tiles_kernel<<<1, 1024, 0, st>>>(pl);
+        EVREP_LAUNCH_CHECK();
+        taf_tile_bits_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
+        EVREP_LAUNCH_CHECK();
+        if (grid > 0) {
+            taf_bucket_kernel<true><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins, vec_ok);
+            EVREP_LAUNCH_CHECK();
+        }
+    } else {
+        EVREP_CUDA(cudaMemsetAsync(s + L.o_tiletotal, 0, (size_t)(L.o_origins - L.o_tiletotal), st));   // totals, bases, tile bits
+    }
+
+    return EVREP_OK;
+}
+
+}  // namespace evrep

@@ -38,6 +38,15 @@ inline int grid_for(int64_t work, int per_thread = 1, int block = kBlock, int wa
     return (int)(need < cap ? need : cap);
 }
 
+// v / 5 * 255 (generate_eventvolume.py:37) without the IEEE-division subroutine: one Newton
+// correction of v * RN(1/5) is the correctly rounded quotient for every finite v away from the
+// denormal range, so the two roundings of the reference are reproduced.
+__device__ __forceinline__ float div5_mul255(float v) {
+    const float q = v * 0.2f;
+    const float r = fmaf(-q, 5.0f, v);
+    return fmaf(r, 0.2f, q) * 255.0f;
+}
+
 // ---- event loaders ---------------------------------------------------------------
 // One decoded event as the encoders see it: grid coordinates (already mapped), the
 // polarity, and `ok` = inside the H x W grid with p in {0,1}.

@@ -232,12 +232,6 @@ ev_splat_kernel(Loader ev, TimeNorm<Loader> tn, int64_t n, int H, int W, int K, 
     }
 }
 
-__device__ __forceinline__ float div5_mul255(float v) {      // v / 5 * 255 with a correctly rounded quotient
-    const float q = v * 0.2f;
-    const float r = fmaf(-q, 5.0f, v);
-    return fmaf(r, 0.2f, q) * 255.0f;
-}
-
 __global__ void __launch_bounds__(kBlock)
 ev_scale_kernel(float4* __restrict__ acc4, int64_t n4, float* __restrict__ acc, int64_t n) {   // :37  / 5 * 255
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
