@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
             while not self._halt.is_set():
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 self.mask |= pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                self._halt.wait(0.05)
+                self._halt.wait(0.002)
         except Exception as exc:          # clocks are evidence, not a dependency
             self.error = repr(exc)
 
@@ -121,7 +121,7 @@ def cpu_reference_leg(t, x, y, p, windows, sample_windows, repeats=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=10.0, help="recording length (default: the 100 M-event workload)")
