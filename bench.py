@@ -71,12 +71,15 @@ def plan(records, seconds):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons sampled with NVML during the timed region."""
+    """SM clock / throttle reasons sampled with NVML while a timed region is armed.
+    The thread (and NVML) is brought up before the warm-up so that the first sample
+    lands inside the timed region, not after it."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.mask, self.max_mhz, self._halt = index, [], 0, None, threading.Event()
+        self.index, self.max_mhz, self._halt, self._armed = index, None, threading.Event(), threading.Event()
+        self.regions, self._region, self.error = {}, None, None
 
     def run(self):
         try:
@@ -85,17 +88,32 @@ class ClockSampler(threading.Thread):
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             while not self._halt.is_set():
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                self.mask |= pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                self._halt.wait(0.002)
+                if not self._armed.wait(0.05):
+                    continue
+                region = self.regions[self._region]
+                region["mhz"].append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                region["mask"] |= pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self._halt.wait(0.001)
         except Exception as exc:          # clocks are evidence, not a dependency
             self.error = repr(exc)
 
+    def arm(self, region):
+        self.regions.setdefault(region, {"mhz": [], "mask": 0})
+        self._region = region
+        self._armed.set()
+
+    def disarm(self):
+        self._armed.clear()
+
     def stop(self):
         self._halt.set()
+        self._armed.set()
         self.join(timeout=2)
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": [n for bit, n in self.REASONS.items() if self.mask & bit], "samples": len(self.samples)}
+
+    def report(self, region):
+        r = self.regions.get(region, {"mhz": [], "mask": 0})
+        return {"sm_mhz": statistics.median(r["mhz"]) if r["mhz"] else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for bit, n in self.REASONS.items() if r["mask"] & bit], "samples": len(r["mhz"])}
 
 
 def cpu_reference_leg(t, x, y, p, windows, sample_windows, repeats=1):
@@ -195,19 +213,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.arm("device")
     start.record()
     for i in range(args.steps):
         step(pairs[i])
     stop.record()
     barrier()
-    clocks = sampler.stop()
+    sampler.disarm()
     ms = start.elapsed_time(stop) / args.steps
     tile_ms = statistics.mean(a.elapsed_time(b) for a, b in pairs)
 
@@ -258,11 +277,13 @@ def main():
         barrier()
         s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_e2e = max(2, min(args.steps, 3))
+        sampler.arm("e2e")
         s2.record()
         for _ in range(n_e2e):
             e2e_step()
         e2.record()
         barrier()
+        sampler.disarm()
         e2e_ms = s2.elapsed_time(e2) / n_e2e
         if world > 1:
             tmax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -272,6 +293,10 @@ def main():
                "h2d_bytes_per_step": int(raw_host.numel()), "d2h_bytes_per_step": int(u8_host.numel()),
                "path": "pinned .dat bytes -> H2D -> decode -> taf_stream -> leaky uint8 [K,2,Ht,Wt] -> D2H, "
                        "24-window chunks on three streams (generate_taf.HostPipeline)"}
+
+    sampler.stop()
+    clocks = sampler.report("device")
+    clocks["e2e_region"] = sampler.report("e2e")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
