@@ -4,13 +4,25 @@ namespace evrep {
 
 // ---- Event Volume over whole streams ----------------------------------------------------------
 // generate_eventvolume.py:15-42 for a list of non-overlapping windows: the same bucketing (one
-// "bin" per window, d = t - t0) feeds one CTA per sensor tile.  The tile's [2K][P] float
-// accumulator lives in shared memory: splat (shared-memory float atomics), then one pass that
-// reads, clears, scales by /5*255 and stores 16 bytes per thread to the tensor (rows are contiguous).
-// Two CTAs per SM, so one tile's output pass overlaps the other tile's splat.  Records arrive through the same ring of TMA bulk copies as in the TAF kernel.
+// "bin" per window, d = t - t0) feeds one CTA per sensor tile.  The tile's [2K][P] accumulator
+// lives in shared memory: splat, then one pass that reads, clears, scales by /5*255 and stores
+// 16 bytes per thread to the tensor (rows are contiguous).  Two CTAs per SM, so one tile's
+// output pass overlaps the other tile's splat.  Records arrive through the same ring of TMA
+// bulk copies as in the TAF kernel.
+//
+// Accumulator format.  Shared-memory float atomics are compare-and-swap loops and the events of
+// a moving edge pile onto a handful of cells, so the weights (f32, computed exactly as the
+// reference does) are summed in fixed point with native u32 atomics instead: a cell is a u32
+// `lo` in units of 2^-27 (wraps at 32) plus a u8 count of wraps, value = 32 hi + lo 2^-27.
+// A weight converts to within 2^-28 (absolute); the sum itself is exact and order independent,
+// so the output is deterministic.  The reference's own f32 running sum rounds by up to 2^-24 of
+// the partial sum per add, which is the larger error once a cell holds more than one event.
+// The wrap count saturates at 255, i.e. a cell sum of 8160; the reference's on-disk format
+// already saturates at a sum of 5 (uint8 of sum / 5 * 255, generate_eventvolume.py:160).
 constexpr int kEvThreads = 512;
-constexpr int kEvTilesPerSm = 2;        // two CTAs per SM: one splats while the other's bulk store drains
-
+constexpr int kEvTilesPerSm = 2;        // two CTAs per SM: one splats while the other's stores drain
+constexpr float kEvUnit = 134217728.0f; // 2^27
+constexpr float kEvWrap = 32.0f;        // 2^32 / 2^27
 
 struct EvTileParams {
     StreamPlan pl;
@@ -18,17 +30,17 @@ struct EvTileParams {
     int64_t out_stride;
     double tw;             // window length: t_norm = d / tw in float64 (generate_eventvolume.py:141)
     int K;
-    int bulk_out;
+    int vec_out;
 };
 
 struct EvTileSmem {
-    int ring, acc, bars, feed, total;
+    int ring, acc, hi, bars, total;
     __host__ __device__ EvTileSmem(int P, int K) {
         int o = 0;
         ring = o; o += kWsRing * 4;
-        acc = o;  o += 2 * K * P * 4;
+        acc = o;  o += 2 * K * P * 4;      // lo words
+        hi = o;   o += 2 * K * P;          // wrap counts, one byte per cell
         bars = o; o += 64;
-        feed = o; o += (TileSmemWS::kFeedBytes + 15) / 16 * 16;
         total = o;
     }
 };
@@ -39,14 +51,15 @@ ev_tile_kernel(EvTileParams tp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const EvTileSmem lay(pl.P, tp.K);
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + lay.ring);
-    float* acc = reinterpret_cast<float*>(smem_raw + lay.acc);             // [2K][P]
+    uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw + lay.acc);       // [2K][P] lo words
+    uint32_t* acc_hi = reinterpret_cast<uint32_t*>(smem_raw + lay.hi);     // [2K][P] bytes, 4 cells per word
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);
 
-    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int tid = threadIdx.x, tile = blockIdx.x, lane = tid & 31;
     const int K = tp.K, rows = 2 * K;
-    const int64_t HW = (int64_t)pl.H * pl.W;
-    const int64_t pix0 = (int64_t)tile * pl.P;
-    const int npix = (int)min((int64_t)pl.P, HW - pix0);
+    const uint32_t HW = (uint32_t)(pl.H * pl.W), P = (uint32_t)pl.P;
+    const uint32_t pix0 = (uint32_t)tile * P;
+    const uint32_t npix = min(P, HW - pix0);
     const uint32_t* my_off = pl.off_rel + (int64_t)tile * (pl.TB + 1);
     const uint32_t* my_records = pl.records + pl.tile_base[tile];
     const uint32_t list_len = (pl.tile_total[tile] + 3u) & ~3u;
@@ -65,24 +78,36 @@ ev_tile_kernel(EvTileParams tp) {
     __syncthreads();
     if (tid == 0)
         for (int c = 0; c < n_chunks && c < kWsStages; ++c) issue(c);
-    BatchFeed feed;
-    feed.init(smem_raw + lay.feed, &pl, my_off, tid, 0, kEvThreads);       // barrier 0 = the whole CTA
+
+    // Window w is bin w of the plan (one bin per window).  Its record range [off[w], off[w+1])
+    // comes from registers: lane l of every warp holds the bounds of window g*32 + l, and the
+    // next group of 32 is loaded one group ahead.
+    const int n_windows = pl.n_windows;
+    auto load_bounds = [&](int first, uint32_t& lo, uint32_t& hi) {
+        const int w = min(first + lane, n_windows - 1);
+        lo = __ldg(my_off + w); hi = __ldg(my_off + w + 1);
+    };
+    uint32_t b_lo, b_hi, nb_lo = 0, nb_hi = 0;
+    load_bounds(0, b_lo, b_hi);
 
     int ready_chunk = -1, next_refill = kWsStages;
     const float Kf = (float)K;
     const double inv_tw = 1.0 / tp.tw;
-    const int n4 = rows * pl.P / 4;
-    const int p4 = pl.P / 4;                                               // float4 columns per row
-    const int row_first = tid / p4, c4_first = tid - row_first * p4;
-    const int row_step = kEvThreads / p4, c4_step = kEvThreads - row_step * p4;
-    for (int i = tid; i < rows * pl.P; i += kEvThreads) acc[i] = 0.0f;     // afterwards the output pass keeps it clean
+    // output pass: thread walks the float4 cells i = tid + k * kEvThreads of the [2K][P] tile
+    const uint32_t n4 = (uint32_t)rows * P / 4u, p4 = P / 4u;
+    const uint32_t row_first = (uint32_t)tid / p4, c4_first = (uint32_t)tid - row_first * p4;
+    const uint32_t row_step = kEvThreads / p4, c4_step = kEvThreads - row_step * p4;
+    const uint32_t g_first = row_first * HW + c4_first * 4u;              // element offset inside the window tensor
+    const uint32_t g_step = row_step * HW + c4_step * 4u, g_wrap = HW - P;
+    for (uint32_t i = tid; i < (uint32_t)rows * P; i += kEvThreads) acc[i] = 0u;     // afterwards the output pass keeps it clean
+    for (uint32_t i = tid; i < n4; i += kEvThreads) acc_hi[i] = 0u;
     __syncthreads();
-    for (int j = 0; j < pl.n_batches; ++j) {
-        const Batch meta = feed.begin(j);
-        const int jb = j & 1;
-        // every window is one bin; a zero-bin window still emits an all-zero tensor
-        const uint32_t o0 = meta.nb > 0 ? feed.s_off[jb * (kBatchBins + 1)] : 0u;
-        const uint32_t o1 = meta.nb > 0 ? feed.s_off[jb * (kBatchBins + 1) + meta.nb] : 0u;
+    for (int w = 0; w < n_windows; ++w) {
+        if ((w & 31) == 0) {
+            if (w) { b_lo = nb_lo; b_hi = nb_hi; }
+            if (w + 32 < n_windows) load_bounds(w + 32, nb_lo, nb_hi);
+        }
+        const uint32_t o0 = __shfl_sync(0xFFFFFFFFu, b_lo, w & 31), o1 = __shfl_sync(0xFFFFFFFFu, b_hi, w & 31);
         uint32_t cur = o0;
         while (cur < o1) {
             const uint32_t avail = (uint32_t)next_refill * kWsChunkRecords;     // records requested so far
@@ -92,8 +117,16 @@ ev_tile_kernel(EvTileParams tp) {
                 ++ready_chunk;
                 mbar_wait(full + (ready_chunk % kWsStages), (uint32_t)(ready_chunk / kWsStages) & 1u);
             }
-            for (uint32_t r = cur + tid; r < limit; r += kEvThreads) {
-                const uint32_t rec = ring[r & (kWsRing - 1)];
+            // A warp does not take 32 consecutive records (a burst on one pixel would serialise on
+            // one cell): lane l walks records l * stride + warp + 16 k; stride is odd, so the ring
+            // reads stay free of bank conflicts.
+            const uint32_t span = limit - cur;
+            const uint32_t stride = ((span + 31u) >> 5) | 1u;
+            const uint32_t lane_base = (uint32_t)lane * stride;
+            for (uint32_t q = (uint32_t)(tid >> 5); q < stride; q += kEvThreads / 32) {
+                const uint32_t idx = lane_base + q;
+                if (idx >= span) continue;
+                const uint32_t rec = ring[(cur + idx) & (kWsRing - 1)];
                 const uint32_t lp = (rec >> 1) & 0x1FFFu, pol = rec & 1u;
                 // (t - t0) / tw in float64 (:141) then .float() (:23): reciprocal + one Newton step
                 const double dd = (double)(rec >> 14);
@@ -105,8 +138,17 @@ ev_tile_kernel(EvTileParams tp) {
                 for (int d = 0; d < 2; ++d) {                                     // centres c0, c0 + 1 (1..K)
                     const int c = c0 + d;
                     if (c < 1 || c > K) continue;
-                    const float w = 1.0f - fabsf((float)c - ts);
-                    if (w > 0.0f) atomicAdd(acc + (2 * (c - 1) + (1 - (int)pol)) * pl.P + lp, w);
+                    const float wgt = 1.0f - fabsf((float)c - ts);
+                    if (wgt > 0.0f) {
+                        const uint32_t cell = (uint32_t)(2 * (c - 1) + (1 - (int)pol)) * P + lp;
+                        const uint32_t fx = __float2uint_rn(wgt * kEvUnit);       // wgt <= 1
+                        const uint32_t old = atomicAdd(acc + cell, fx);
+                        if (old + fx < old) {                                     // lo wrapped: count it
+                            const uint32_t sh = (cell & 3u) * 8u;
+                            const uint32_t before = atomicAdd(acc_hi + (cell >> 2), 1u << sh);
+                            if (((before >> sh) & 0xFFu) == 0xFFu) atomicSub(acc_hi + (cell >> 2), 1u << sh);   // saturate
+                        }
+                    }
                 }
             }
             cur = limit;
@@ -127,34 +169,40 @@ ev_tile_kernel(EvTileParams tp) {
                 next_refill = drained + kWsStages;
             }
         }
-        if (meta.flags & 2) {
-            // read, clear and scale the accumulator (:37  / 5 * 255), 16 bytes per thread straight
-            // to global memory: each row is contiguous, so every warp store is 512 contiguous bytes
-            float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
-            if (tp.bulk_out) {
-                // (row, column) of float4 number i = tid + k * kEvThreads, advanced without divisions
-                int row = row_first, c4 = c4_first;
-                for (int i = tid; i < n4; i += kEvThreads) {
-                    const int lp = c4 * 4;
-                    float4 v = reinterpret_cast<float4*>(acc)[i];
-                    reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (lp < npix) {
-                        v.x = div5_mul255(v.x); v.y = div5_mul255(v.y); v.z = div5_mul255(v.z); v.w = div5_mul255(v.w);
-                        __stcs(reinterpret_cast<float4*>(o + (int64_t)row * HW + lp), v);
-                    }
-                    row += row_step; c4 += c4_step;
-                    if (c4 >= p4) { c4 -= p4; ++row; }
+        // read, clear and scale the accumulator (:37  / 5 * 255); each row of the tile is
+        // contiguous in the tensor, so every warp store is 512 contiguous bytes
+        float* o = tp.out + (int64_t)w * tp.out_stride + pix0;
+        auto value = [](uint32_t lo, uint32_t wraps) -> float {
+            return div5_mul255(fmaf((float)wraps, kEvWrap, (float)lo * (1.0f / kEvUnit)));
+        };
+        if (tp.vec_out) {
+            uint32_t c4 = c4_first, g = g_first;
+            for (uint32_t i = tid; i < n4; i += kEvThreads) {
+                const uint4 lo = reinterpret_cast<uint4*>(acc)[i];
+                const uint32_t wr = acc_hi[i];
+                reinterpret_cast<uint4*>(acc)[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (wr) acc_hi[i] = 0u;
+                if (c4 * 4u < npix) {
+                    float4 v;
+                    v.x = value(lo.x, wr & 0xFFu); v.y = value(lo.y, (wr >> 8) & 0xFFu);
+                    v.z = value(lo.z, (wr >> 16) & 0xFFu); v.w = value(lo.w, wr >> 24);
+                    __stcs(reinterpret_cast<float4*>(o + g), v);
                 }
-            } else {
-                for (int i = tid; i < rows * pl.P; i += kEvThreads) {
-                    const int row = i / pl.P, lp = i - row * pl.P;
-                    const float v = acc[i];
-                    acc[i] = 0.0f;
-                    if (lp < npix) __stcs(o + (int64_t)row * HW + lp, div5_mul255(v));
-                }
+                c4 += c4_step; g += g_step;
+                if (c4 >= p4) { c4 -= p4; g += g_wrap; }
             }
+        } else {
+            for (uint32_t i = tid; i < (uint32_t)rows * P; i += kEvThreads) {
+                const uint32_t row = i / P, lp = i - row * P;
+                const uint32_t lo = acc[i];
+                const uint32_t wr = (acc_hi[i >> 2] >> ((i & 3u) * 8u)) & 0xFFu;
+                acc[i] = 0u;
+                if (lp < npix) __stcs(o + (int64_t)row * HW + lp, value(lo, wr));
+            }
+            __syncthreads();                                       // the byte counters share words
+            for (uint32_t i = tid; i < n4; i += kEvThreads) acc_hi[i] = 0u;
         }
-        feed.end(j);                                               // also orders the clears before the next splat
+        __syncthreads();                                           // clears are ordered before the next splat
     }
 }
 
@@ -196,8 +244,8 @@ int evrep_event_volume_stream(const uint32_t* t, const uint16_t* x, const uint16
     if (smem > 232448) return EVREP_ERR_RANGE;
     EvTileParams tp;
     tp.pl = pl; tp.out = out; tp.out_stride = out_stride; tp.tw = (double)tw; tp.K = K;
-    tp.bulk_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                   L.P % 4 == 0) ? 1 : 0;
+    tp.vec_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                  L.P % 4 == 0) ? 1 : 0;
     EVREP_CUDA(cudaFuncSetAttribute(ev_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ev_tile_kernel<<<L.n_tiles, kEvThreads, smem, st>>>(tp);
     EVREP_LAUNCH_CHECK();

@@ -170,6 +170,34 @@ def test_event_volume_stream_matches_oracle_and_single_window_path(K):
         assert close(got[i], oe.event_volume(e, (512, 640), K)), i
 
 
+def test_event_volume_stream_hot_pixels_and_determinism():
+    """Cells that collect thousands of events (the fixed-point accumulator wraps several times)
+    still match the oracle, and two runs are bit-identical."""
+    rng = np.random.default_rng(5)
+    n = 60000
+    t = np.sort(rng.integers(0, 100000, n)).astype(np.uint32)
+    x = rng.integers(0, 304, n).astype(np.uint16)
+    y = rng.integers(0, 240, n).astype(np.uint16)
+    p = rng.integers(0, 2, n).astype(np.uint8)
+    hot = rng.random(n) < 0.5                       # half of the stream fires on three pixels
+    which = rng.integers(0, 3, n)
+    x[hot] = np.array([7, 150, 303], dtype=np.uint16)[which[hot]]
+    y[hot] = np.array([0, 120, 239], dtype=np.uint16)[which[hot]]
+    p[hot & (which == 1)] = 1
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    tw = 100000
+    windows = [(0, n, 0)]
+    got = ops.event_volume_stream(ev, windows, tw, (240, 304), 5).clone()
+    again = ops.event_volume_stream(ev, windows, tw, (240, 304), 5)
+    assert torch.equal(got, again)
+    from helpers import staged
+    e = staged(t, x, y, p, 0, n)
+    e[:, 2] = (e[:, 2] - 0) / tw
+    want = oe.event_volume(e, (240, 304), 5)
+    assert float(want.max()) > 512 / 5 * 255                      # a cell sum beyond one wrap of the low word
+    assert close(got[0], want)
+
+
 def test_single_role_kernel_equals_warp_specialised(monkeypatch):
     """The non-specialised tile kernel (fallback when the staging tile does not fit next to two
     accumulator buffers) gives bit-identical results."""
