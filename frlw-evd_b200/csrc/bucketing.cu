@@ -117,8 +117,8 @@ struct BucketSmem {
     int lutx, luty, hist, loff, gbase, sorted, skey, total;
     __host__ __device__ BucketSmem(int lut_w, int lut_h, int nh, bool scatter) {
         int o = 0;
-        lutx = o;  o += (lut_w * 2 + 15) / 16 * 16;
-        luty = o;  o += (lut_h * 2 + 15) / 16 * 16;
+        lutx = o;  o += (lut_w * 4 + 15) / 16 * 16;      // column of a raw x (u32), kOffGrid when dropped
+        luty = o;  o += (lut_h * 4 + 15) / 16 * 16;      // first pixel of the row of a raw y, kOffGrid when dropped
         hist = o;  o += nh * 4;
         loff = o;  o += scatter ? nh * 4 : 0;
         gbase = o; o += scatter ? nh * 4 : 0;
@@ -140,10 +140,9 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
                   const ChunkOrigin* __restrict__ origins, int vec_ok) {
     extern __shared__ __align__(16) unsigned char bsm[];
     const int nh = kLocalBins * pl.n_tiles;
-    const bool use_lut = ev.xmap != nullptr && ev.ymap != nullptr;
-    const BucketSmem lay(use_lut ? lut_w : 0, use_lut ? lut_h : 0, nh, kScatter);
-    uint16_t* s_lutx = reinterpret_cast<uint16_t*>(bsm + lay.lutx);
-    uint16_t* s_luty = reinterpret_cast<uint16_t*>(bsm + lay.luty);
+    const BucketSmem lay(lut_w, lut_h, nh, kScatter);
+    uint32_t* s_col = reinterpret_cast<uint32_t*>(bsm + lay.lutx);
+    uint32_t* s_row = reinterpret_cast<uint32_t*>(bsm + lay.luty);
     uint32_t* hist = reinterpret_cast<uint32_t*>(bsm + lay.hist);
     uint32_t* loff = reinterpret_cast<uint32_t*>(bsm + lay.loff);
     uint32_t* gbase = reinterpret_cast<uint32_t*>(bsm + lay.gbase);
@@ -151,11 +150,22 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
     uint16_t* skey = reinterpret_cast<uint16_t*>(bsm + lay.skey);
     __shared__ uint32_t s_tmp[kBucketThreads / 32 + 1];
 
-    if (use_lut) {
-        for (int i = threadIdx.x; i < lut_w; i += kBucketThreads) s_lutx[i] = ev.xmap[i];
-        for (int i = threadIdx.x; i < lut_h; i += kBucketThreads) s_luty[i] = ev.ymap[i];
+    // Coordinate tables: raw x -> grid column, raw y -> first pixel of the grid row; entries that
+    // leave the grid hold kOffGrid, so that "row + column < H W" is the only range test per event.
+    // Without user LUTs the tables are the identity over the grid.
+    const uint32_t W = pl.W, H = pl.H, HW = W * H;
+    constexpr uint32_t kOffGrid = 0x40000000u;
+    for (int i = threadIdx.x; i < lut_w; i += kBucketThreads) {
+        const uint32_t xm = ev.xmap ? ev.xmap[i] : (uint32_t)i;
+        s_col[i] = xm < W ? xm : kOffGrid;
     }
-    const uint32_t W = pl.W, H = pl.H;
+    for (int i = threadIdx.x; i < lut_h; i += kBucketThreads) {
+        const uint32_t ym = ev.ymap ? ev.ymap[i] : (uint32_t)i;
+        s_row[i] = ym < H ? ym * W : kOffGrid;
+    }
+    const uint32_t col_addr = smem_u32(s_col), row_addr = smem_u32(s_row);
+    const uint32_t n_cols = (uint32_t)lut_w, n_rows = (uint32_t)lut_h;
+    const uint32_t tile_mul = pl.tile_mul, P = (uint32_t)pl.P, n_tiles = (uint32_t)pl.n_tiles;
 
     for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const int64_t c0 = ev_first + (int64_t)chunk * (kBucketThreads * kBucketPerThread);
@@ -171,34 +181,36 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
         // all global loads of the chunk are issued before any of them is used
         const bool fast = single && (c1 - c0) == kBucketThreads * kBucketPerThread &&
                           wi.start >= 0 && wi.start <= 0xFFFFFFFFll;
-        // per event: timestamp and x | y << 14 | p << 28 (the .dat word), kBad when out of range
-        constexpr uint32_t kBad = 0xFFFFFFFFu;
-        auto pack = [](uint32_t x, uint32_t y, uint32_t p) -> uint32_t {
-            return (((x | y) >> 14) | (p >> 1)) ? kBad : (x | (y << 14) | (p << 28));
-        };
-        uint32_t tt[kBucketPerThread], xyp[kBucketPerThread];
+        // per event: timestamp, x | y << 16, and the polarity bytes four to a word (0xFF = no event)
+        uint32_t tt[kBucketPerThread], xy[kBucketPerThread], pw[kBucketPerThread / 4];
+        static_assert(kBucketPerThread % 4 == 0, "events are handled in groups of 4");
         if (fast && vec_ok) {
             // 4 consecutive events per 128/64/64/32-bit load (c0 is a multiple of 4 events)
-            static_assert(kBucketPerThread % 4 == 0, "vector path loads events in groups of 4");
 #pragma unroll
             for (int g = 0; g < kBucketPerThread / 4; ++g) {
                 const int64_t base = c0 + ((int64_t)g * kBucketThreads + threadIdx.x) * 4;
                 const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(ev.t + base));
                 const uint2 x4 = __ldg(reinterpret_cast<const uint2*>(ev.x + base));
                 const uint2 y4 = __ldg(reinterpret_cast<const uint2*>(ev.y + base));
-                const uint32_t p4 = __ldg(reinterpret_cast<const uint32_t*>(ev.p + base));
+                pw[g] = __ldg(reinterpret_cast<const uint32_t*>(ev.p + base));
                 tt[4 * g + 0] = t4.x; tt[4 * g + 1] = t4.y; tt[4 * g + 2] = t4.z; tt[4 * g + 3] = t4.w;
-                xyp[4 * g + 0] = pack(x4.x & 0xFFFFu, y4.x & 0xFFFFu, p4 & 0xFFu);
-                xyp[4 * g + 1] = pack(x4.x >> 16, y4.x >> 16, (p4 >> 8) & 0xFFu);
-                xyp[4 * g + 2] = pack(x4.y & 0xFFFFu, y4.y & 0xFFFFu, (p4 >> 16) & 0xFFu);
-                xyp[4 * g + 3] = pack(x4.y >> 16, y4.y >> 16, p4 >> 24);
+                xy[4 * g + 0] = __byte_perm(x4.x, y4.x, 0x5410); xy[4 * g + 1] = __byte_perm(x4.x, y4.x, 0x7632);
+                xy[4 * g + 2] = __byte_perm(x4.y, y4.y, 0x5410); xy[4 * g + 3] = __byte_perm(x4.y, y4.y, 0x7632);
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < kBucketPerThread; ++k) {
-                const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
-                xyp[k] = kBad;
-                if (i < c1) { tt[k] = __ldg(ev.t + i); xyp[k] = pack(__ldg(ev.x + i), __ldg(ev.y + i), __ldg(ev.p + i)); }
+            for (int g = 0; g < kBucketPerThread / 4; ++g) {
+                uint32_t pol4 = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 4 * g + e;
+                    const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
+                    uint32_t pv = 0xFFu;
+                    tt[k] = 0; xy[k] = 0;
+                    if (i < c1) { tt[k] = __ldg(ev.t + i); xy[k] = __ldg(ev.x + i) | ((uint32_t)__ldg(ev.y + i) << 16); pv = __ldg(ev.p + i); }
+                    pol4 |= pv << (8 * e);
+                }
+                pw[g] = pol4;
             }
         }
 
@@ -211,7 +223,7 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
         auto deposit = [&](int k, uint32_t tile, int gbin) {
             const uint32_t lb = (uint32_t)(gbin - gb0);
             if (lb < (uint32_t)kLocalBins) {
-                const uint32_t key = lb * (uint32_t)pl.n_tiles + tile;
+                const uint32_t key = lb * n_tiles + tile;
                 if (kScatter) slot[k] = (key << 12) | atomicAdd(&hist[key], 1u);
                 else atomicAdd(&hist[key], 1u);
             } else {                          // unsorted input or a very sparse stream: go straight to global
@@ -221,18 +233,16 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
                 else { atomicAdd(cursor, 1u); pl.bin_any[gbin] = 1u; }
             }
         };
-        // map raw coordinates to the grid; false when the event is to be dropped
-        auto locate = [&](int k, uint32_t& pix) -> bool {
-            uint32_t xm = xyp[k] & 0x3FFFu, ym = (xyp[k] >> 14) & 0x3FFFu;
-            bool ok = xyp[k] != kBad;
-            if (use_lut) {
-                ok = ok && xm < (uint32_t)lut_w && ym < (uint32_t)lut_h;
-                xm = s_lutx[min(xm, (uint32_t)lut_w - 1u)];
-                ym = s_luty[min(ym, (uint32_t)lut_h - 1u)];
-            }
-            pix = ym * W + xm;
-            return ok && xm < W && ym < H;
+        // grid pixel and polarity of event k; false when the event is to be dropped
+        auto locate = [&](int k, uint32_t& pix, uint32_t& pol) -> bool {
+            const uint32_t xv = xy[k] & 0xFFFFu, yv = xy[k] >> 16;
+            pol = (pw[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+            if (xv >= n_cols || yv >= n_rows || pol > 1u) return false;
+            pix = lds_u32(col_addr + xv * 4u) + lds_u32(row_addr + yv * 4u);
+            return pix < HW;
         };
+        // tile of a pixel: one multiply when the host proved the magic number exact for this grid
+        auto tile_of = [&](uint32_t pix) -> uint32_t { return tile_mul ? __umulhi(pix, tile_mul) : pl.div_P.div(pix); };
 
         if (fast) {
             // the whole chunk lies in one window: 32-bit time arithmetic, no bounds checks
@@ -240,12 +250,12 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
 #pragma unroll
             for (int k = 0; k < kBucketPerThread; ++k) {
                 slot[k] = kNone;
-                uint32_t pix;
-                if (!locate(k, pix)) continue;
-                const uint32_t u = tt[k] >= start32 ? tt[k] - start32 : 0u;
+                uint32_t pix, pol;
+                if (!locate(k, pix, pol)) continue;
+                const uint32_t u = max(tt[k], start32) - start32;
                 const uint32_t z = min(pl.div_abin.div(u), zmax);
-                const uint32_t tile = pl.div_P.div(pix);
-                if (kScatter) rec[k] = (min(u - z * pl.abin, kDMax) << 14) | ((pix - tile * pl.P) << 1) | (xyp[k] >> 28);
+                const uint32_t tile = tile_of(pix);
+                if (kScatter) rec[k] = (min(u - z * pl.abin, kDMax) << 14) | ((pix - tile * P) << 1) | pol;
                 deposit(k, tile, wi.binbase + (int)z);
             }
         } else {
@@ -260,12 +270,12 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
                     wi = load_window(pl, w);
                     if (i < wi.begin || wi.nbins <= 0) continue;
                 }
-                uint32_t pix;
-                if (!locate(k, pix)) continue;
+                uint32_t pix, pol;
+                if (!locate(k, pix, pol)) continue;
                 uint32_t z, d;
                 bin_of(pl, wi, tt[k], z, d);
-                const uint32_t tile = pl.div_P.div(pix);
-                rec[k] = (d << 14) | ((pix - tile * pl.P) << 1) | (xyp[k] >> 28);
+                const uint32_t tile = tile_of(pix);
+                rec[k] = (d << 14) | ((pix - tile * P) << 1) | pol;
                 deposit(k, tile, wi.binbase + (int)z);
             }
         }
@@ -514,6 +524,11 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
     pl.n_tiles = L.n_tiles; pl.P = L.P; pl.H = H; pl.W = W;
     pl.div_abin = FastDiv::make((uint32_t)abin);
     pl.div_P = FastDiv::make((uint32_t)L.P);
+    {   // pix / P as one multiply-high: exact while pix * (mul * P - 2^32) < 2^32
+        const uint64_t mul = (1ull << 32) / (uint64_t)L.P + 1;
+        const uint64_t err = mul * (uint64_t)L.P - (1ull << 32);
+        pl.tile_mul = (mul < (1ull << 32) && (uint64_t)H * W * err < (1ull << 32)) ? (uint32_t)mul : 0u;
+    }
     pl.abin = (uint32_t)abin;
 
     if (TB > 0) {
@@ -526,10 +541,13 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
         const int64_t n_chunks = (ev_last - ev_first + per_cta - 1) / per_cta;
         if (n_chunks >= (1ll << 31)) return EVREP_ERR_RANGE;
         const int grid = (int)(n_chunks < 2ll * sm_count() ? n_chunks : 2ll * sm_count());
+        // coordinate tables of the bucketing kernels: the user LUTs over the sensor, or the identity over the grid
         const bool use_lut = xmap && ymap;
+        const int lut_w = use_lut ? sensor_w : W, lut_h = use_lut ? sensor_h : H;
         const int nh = kLocalBins * L.n_tiles;
-        const size_t smem_count = (size_t)BucketSmem(use_lut ? sensor_w : 0, use_lut ? sensor_h : 0, nh, false).total;
-        const size_t smem_scatter = (size_t)BucketSmem(use_lut ? sensor_w : 0, use_lut ? sensor_h : 0, nh, true).total;
+        const size_t smem_count = (size_t)BucketSmem(lut_w, lut_h, nh, false).total;
+        const size_t smem_scatter = (size_t)BucketSmem(lut_w, lut_h, nh, true).total;
+        if (smem_scatter > 100 * 1024) return EVREP_ERR_RANGE;          // two CTAs per SM
         EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
         EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
         SoA ev{t, x, y, p, xmap, ymap};
@@ -537,7 +555,7 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
         if (grid > 0) {
             taf_chunk_origin_kernel<<<(int)((n_chunks + 255) / 256), 256, 0, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, origins);
             EVREP_LAUNCH_CHECK();
-            taf_bucket_kernel<false><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins, vec_ok);
+            taf_bucket_kernel<false><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok);
             EVREP_LAUNCH_CHECK();
         }
         taf_scan_rows_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
@@ -547,7 +565,7 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
         taf_tile_bits_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
         EVREP_LAUNCH_CHECK();
         if (grid > 0) {
-            taf_bucket_kernel<true><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, sensor_w, sensor_h, origins, vec_ok);
+            taf_bucket_kernel<true><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok);
             EVREP_LAUNCH_CHECK();
         }
     } else {

@@ -67,10 +67,17 @@ struct StreamPlan {       // device pointers into the scratch buffer
     int n_windows, n_batches, TB, n_tiles, P, H, W;
     FastDiv div_abin, div_P;
     uint32_t abin;
+    uint32_t tile_mul;    // pix / P == umulhi(pix, tile_mul) for every pixel of the grid, or 0 (use div_P)
 };
 
 // ---- mbarrier / TMA bulk-copy primitives (PTX) --------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {      // read-only tables: free to be scheduled
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
