@@ -401,6 +401,13 @@ taf_tile_bits_kernel(StreamPlan pl) {
     }
 }
 
+// Window / batch tables are handed to the device as by-value kernel arguments (see prepare_stream).
+struct MetaPiece { uint32_t words[960]; };          // 3840 bytes, inside the 4 KB argument limit
+__global__ void __launch_bounds__(256)
+meta_upload_kernel(const __grid_constant__ MetaPiece piece, uint32_t* __restrict__ dst, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = piece.words[i];
+}
+
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n_batches, Layout& L, int tiles_per_sm) {
@@ -504,8 +511,16 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
     hbb[n_windows] = base;
     memcpy(meta.data() + L.o_batches, batches.data(), batches.size() * sizeof(Batch));
     char* s = reinterpret_cast<char*>(scratch);
-    EVREP_CUDA(cudaMemcpyAsync(s, meta.data(), (size_t)L.meta_bytes, cudaMemcpyHostToDevice, st));
-    // pageable source: the copy has been staged when the call returns, `meta` may die
+    // The tables travel as kernel arguments, not as a host->device copy: a copy would queue on
+    // the copy engine behind whatever bulk transfer the caller has in flight on another stream
+    // (the event payload of the next chunk in generate_taf.HostPipeline) and stall this stream.
+    for (int64_t done = 0; done < L.meta_bytes; done += (int64_t)sizeof(MetaPiece)) {
+        MetaPiece piece;
+        const int64_t n = L.meta_bytes - done < (int64_t)sizeof(MetaPiece) ? L.meta_bytes - done : (int64_t)sizeof(MetaPiece);
+        memcpy(piece.words, meta.data() + done, (size_t)n);
+        meta_upload_kernel<<<1, 256, 0, st>>>(piece, reinterpret_cast<uint32_t*>(s + done), (int)(n / 4));
+        EVREP_LAUNCH_CHECK();
+    }
 
     pl.w_begin = reinterpret_cast<const int64_t*>(s + L.o_wbegin);
     pl.w_end = reinterpret_cast<const int64_t*>(s + L.o_wend);
