@@ -187,6 +187,8 @@ def main():
     from frlw_evd_b200 import ops, synth
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    from frlw_evd_b200.affinity import bind_to_device
+    placement = bind_to_device(local) if world > 1 else {"bound": False, "how": "single process"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -318,7 +320,7 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu,
-            "windows": nw, "events_in_windows_per_gpu": n_in_windows,
+            "windows": nw, "events_in_windows_per_gpu": n_in_windows, "host_placement": placement,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -144,6 +144,9 @@ def main(argv=None):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("frlw_evd_b200.multi_gpu needs CUDA devices (no CPU fallback)")
+    if world > 1:
+        from .affinity import bind_to_device
+        bind_to_device(local_rank)          # pinned buffers on the GPU's NUMA node
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
