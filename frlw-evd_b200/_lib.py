@@ -27,6 +27,11 @@ class EvWindow(ctypes.Structure):
     _fields_ = [("ev_begin", c_int64), ("ev_end", c_int64), ("t0", c_int64)]
 
 
+class SaeWindow(ctypes.Structure):
+    """``evrep_sae_window`` (include/evrep.h)."""
+    _fields_ = [("ev_begin", c_int64), ("ev_end", c_int64), ("now", c_int64), ("t_first", c_int64), ("t_last", c_int64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/evrep.h declares
 SIGNATURES = {
     "evrep_version": (c_int, []),
@@ -55,6 +60,10 @@ SIGNATURES = {
     "evrep_event_volume_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "evrep_event_volume_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int64, c_int, c_int, c_int, P, P, c_int, c_int,
                                           P, c_int64, P, c_int64, P]),
+    "evrep_sae_stream_scratch_bytes": (c_int64, [c_int64, P, c_int, c_int, c_int]),
+    "evrep_sae_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int, P, c_int64,
+                                 P, c_int64, P]),
+    "evrep_sae_decay_u8_batch": (c_int, [P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P]),
     "evrep_nearest_resize": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "evrep_quantize_u8": (c_int, [P, c_int64, c_int, P, P]),
     "evrep_taf_leaky_u8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),

@@ -408,6 +408,18 @@ meta_upload_kernel(const __grid_constant__ MetaPiece piece, uint32_t* __restrict
     for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = piece.words[i];
 }
 
+int upload_words(const uint32_t* host, int64_t n_words, uint32_t* dst, cudaStream_t st) {
+    constexpr int64_t kPiece = (int64_t)(sizeof(MetaPiece) / 4);
+    for (int64_t done = 0; done < n_words; done += kPiece) {
+        MetaPiece piece;
+        const int64_t n = n_words - done < kPiece ? n_words - done : kPiece;
+        memcpy(piece.words, host + done, (size_t)n * 4);
+        meta_upload_kernel<<<1, 256, 0, st>>>(piece, dst + done, (int)n);
+        EVREP_LAUNCH_CHECK();
+    }
+    return EVREP_OK;
+}
+
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n_batches, Layout& L, int tiles_per_sm) {
@@ -514,13 +526,8 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
     // The tables travel as kernel arguments, not as a host->device copy: a copy would queue on
     // the copy engine behind whatever bulk transfer the caller has in flight on another stream
     // (the event payload of the next chunk in generate_taf.HostPipeline) and stall this stream.
-    for (int64_t done = 0; done < L.meta_bytes; done += (int64_t)sizeof(MetaPiece)) {
-        MetaPiece piece;
-        const int64_t n = L.meta_bytes - done < (int64_t)sizeof(MetaPiece) ? L.meta_bytes - done : (int64_t)sizeof(MetaPiece);
-        memcpy(piece.words, meta.data() + done, (size_t)n);
-        meta_upload_kernel<<<1, 256, 0, st>>>(piece, reinterpret_cast<uint32_t*>(s + done), (int)(n / 4));
-        EVREP_LAUNCH_CHECK();
-    }
+    rc = upload_words(reinterpret_cast<const uint32_t*>(meta.data()), L.meta_bytes / 4, reinterpret_cast<uint32_t*>(s), st);
+    if (rc) return rc;
 
     pl.w_begin = reinterpret_cast<const int64_t*>(s + L.o_wbegin);
     pl.w_end = reinterpret_cast<const int64_t*>(s + L.o_wend);

@@ -197,6 +197,8 @@ struct Layout {
 
 int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n_batches, Layout& L, int tiles_per_sm = 1);
 int64_t batches_upper_bound(int n_windows, int64_t TB);
+// Small host table -> device memory as kernel arguments (no copy engine involved; see prepare_stream).
+int upload_words(const uint32_t* host, int64_t n_words, uint32_t* dst, cudaStream_t st);
 
 // Validates the window list, uploads the window / batch tables and runs the bucketing passes.
 // On return `pl` describes the bucketed records of every (tile, bin).

@@ -69,6 +69,49 @@ def encode_recording(rec: DeviceRecording, labels, geom: Geometry, mode="train")
         yield label, u8
 
 
+def plan_windows(loader, labels):
+    """The driver's window of every label (:147-175) as ``(label, ev_begin, ev_end)``; in test
+    mode the reference also encodes two shorter sub-windows first, which only time the encoder:
+    they are subsets of the largest one and leave the same state behind."""
+    plan = []
+    t_upper, c_upper = -100000000, 0
+    for label in labels:
+        end_time = int(label)
+        end_count = loader.seek_time(end_time)
+        if end_count is None:
+            continue
+        start_time = end_time - EVENTS_WINDOW
+        start_count = loader.seek_time(0 if start_time < 0 else start_time)
+        if start_count is None or start_time < 0:
+            start_count = 0
+        if start_time <= t_upper:
+            start_count = c_upper
+        t_upper, c_upper = label, end_count
+        lo = loader.upper_index(end_time - max(TIME_WINDOW), start_count, end_count)
+        plan.append((label, int(lo), int(end_count)))
+    return plan
+
+
+def encode_recording_stream(rec: DeviceRecording, labels, geom: Geometry, labels_per_call=256):
+    """Whole-recording form of ``encode_recording``: one bucketing + tile-kernel call per
+    ``labels_per_call`` labels instead of two launches per label.  Yields the same
+    ``(label, u8 [L,2,Ht,Wt])``.  Falls back to the per-label path when the windows of
+    consecutive labels overlap (labels less than one window apart never do)."""
+    plan = plan_windows(rec.loader, labels)
+    if any(b[1] < a[2] for a, b in zip(plan, plan[1:])):
+        yield from encode_recording(rec, labels, geom)
+        return
+    time_of = rec.loader.time_of
+    memory = None
+    for first in range(0, len(plan), labels_per_call):
+        part = plan[first:first + labels_per_call]
+        windows = [(lo, hi, label, time_of(lo) if hi > lo else 0, time_of(hi - 1) if hi > lo else 0) for label, lo, hi in part]
+        latest, memory = ops.sae_stream(rec.events, windows, geom.grid, memory, geom.coord_maps)
+        u8 = ops.sae_decay_u8_batch(latest, [w[2] for w in windows], LAMDAS, geom.target, geom.resize_maps)
+        for i, (label, _, _) in enumerate(part):
+            yield label, u8[i]
+
+
 def main(argv=None):
     args = parse_args("gen4", argv)
     geom = Geometry.for_dataset(args.dataset)
@@ -77,7 +120,7 @@ def main(argv=None):
         rec = DeviceRecording(event_file)
         torch.cuda.synchronize()
         tick = time.time()
-        for label, u8 in encode_recording(rec, labels, geom, mode):
+        for label, u8 in encode_recording_stream(rec, labels, geom):
             for j, lam in enumerate(LAMDAS):
                 dump_u8(u8[j], args.target_dir, "SurfaceOfActiveEvents{0}".format(lam), mode,
                         name + "_" + str(label) + ".npy")

@@ -424,6 +424,55 @@ def event_volume_stream(ev: EventStream, windows, tw: int, shape, K: int, maps=N
     return out
 
 
+def sae_stream(ev: EventStream, windows, shape, memory=None, maps=None, out=None):
+    """A1 + A2 for every label of a recording in one call.  ``windows``: ordered, non-overlapping
+    ``(ev_begin, ev_end, now, t_first, t_last)`` -- the events the driver hands to the encoder for
+    label ``now`` and the timestamps of the first / last of them.  Returns ``(latest f32
+    [n_windows, 2, H, W], memory f32 [2, H, W])``: ``latest[w]`` is the reference's ``t_img`` after
+    the merge with ``memory`` (generate_surfaceofactiveevents.py:52), ``memory`` the state after
+    the last window (a new tensor, the argument is not modified)."""
+    _need_cuda(ev.t, memory)
+    H, W = shape
+    nw = len(windows)
+    arr = (_lib.SaeWindow * max(nw, 1))()
+    for i, w in enumerate(windows):
+        arr[i] = _lib.SaeWindow(int(w[0]), int(w[1]), int(w[2]), int(w[3]), int(w[4]))
+    if out is None:
+        out = torch.empty((nw, 2, H, W), dtype=torch.float32, device=ev.device)
+    assert out.is_contiguous()
+    state = memory.clone() if memory is not None else torch.empty((2, H, W), dtype=torch.float32, device=ev.device)
+    need = _lib.load().evrep_sae_stream_scratch_bytes(ev.n, ctypes.cast(arr, ctypes.c_void_p), nw, H, W)
+    if need < 0:
+        _lib.check(int(need), "evrep_sae_stream_scratch_bytes")
+    buf = workspace("taf_stream", need, ev.device)
+    xm, ym = _maps(maps)
+    _lib.call("evrep_sae_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+              ctypes.cast(arr, ctypes.c_void_p), nw, H, W, xm, ym,
+              maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W,
+              _ptr(state), 1 if memory is not None else 0, _ptr(out), 2 * H * W, _ptr(buf), buf.numel(), _stream(ev.device))
+    return out, state
+
+
+def sae_decay_u8_batch(latest, nows, lambdas, target_shape=None, resize_maps=None, out=None):
+    """The decays, nearest resize and uint8 truncation of the SAE driver for all windows of a
+    ``sae_stream`` result: f32 ``[n, 2, H, W]`` -> u8 ``[n, L, 2, Ht, Wt]``."""
+    _need_cuda(latest)
+    n, two, H, W = latest.shape
+    assert two == 2 and latest.is_contiguous()
+    Ht, Wt = target_shape if target_shape is not None else (H, W)
+    if (Ht, Wt) != (H, W) and resize_maps is None:
+        resize_maps = nearest_maps((H, W), (Ht, Wt), latest.device)
+    ys, xs = resize_maps if (Ht, Wt) != (H, W) else (None, None)
+    L = len(lambdas)
+    lam = (ctypes.c_float * L)(*[float(np.float32(v)) for v in lambdas])
+    now_f32 = torch.from_numpy(np.asarray([float(v) for v in nows], dtype=np.float64).astype(np.float32)).to(latest.device)
+    if out is None:
+        out = torch.empty((n, L, 2, Ht, Wt), dtype=torch.uint8, device=latest.device)
+    _lib.call("evrep_sae_decay_u8_batch", _ptr(latest), 2 * H * W, _ptr(now_f32), n, H, W, Ht, Wt, _ptr(ys), _ptr(xs),
+              ctypes.cast(lam, ctypes.c_void_p), L, _ptr(out), _stream(latest.device))
+    return out
+
+
 def count_images_u8(ev: EventStream, sizes: Sequence[int], shape, target_shape, maps=None, resize_maps=None, out=None):
     """Driver form of the count image: the nested last-N windows of one label as uint8
     ``[len(sizes), 2, Ht, Wt]`` in one library call (LUT + nearest resize + truncation fused)."""

@@ -217,6 +217,37 @@ int evrep_event_volume_stream(const uint32_t* t, const uint16_t* x, const uint16
                               float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
                               evrep_stream_t stream);
 
+/* ------------------------------------------------- A1 + A2 over a whole stream -------
+ * generate_surfaceofactiveevents.py:44-69 for every label of a recording in one call: window w
+ * holds the events [ev_begin, ev_end) the driver (:147-175) hands to the encoder for label
+ * `now`; t_first / t_last are the timestamps of its first and last event (ignored when the
+ * window is empty).  Windows are consecutive and do not overlap.  The per-pixel state (latest
+ * float32 timestamp, :54) is carried from window to window in shared memory and written back to
+ * memory_inout (f32 [2,H,W]; read only when has_memory != 0) at the end.
+ * latest_out: f32 [n_windows][2,H,W], window w at latest_out + w * latest_stride -- the value the
+ * reference calls t_img after the merge with `memory` (:52).
+ * evrep_sae_decay_u8_batch: the L decays exp(lambda (t_img - now)) * 255 (:55-63), the nearest
+ * resize and the uint8 truncation of the driver (:186-204) for all windows:
+ * out u8 [n_windows][L,2,Ht,Wt]; now_f32: device array of float32(now) per window. */
+typedef struct {
+    int64_t ev_begin;
+    int64_t ev_end;
+    int64_t now;
+    int64_t t_first;
+    int64_t t_last;
+} evrep_sae_window;
+
+int64_t evrep_sae_stream_scratch_bytes(int64_t n_events, const evrep_sae_window* windows_host, int n_windows,
+                                       int H, int W);
+int evrep_sae_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+                     const evrep_sae_window* windows_host, int n_windows, int H, int W,
+                     const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                     float* memory_inout, int has_memory, float* latest_out, int64_t latest_stride,
+                     void* scratch, int64_t scratch_bytes, evrep_stream_t stream);
+int evrep_sae_decay_u8_batch(const float* latest, int64_t latest_stride, const float* now_f32, int64_t n_windows,
+                             int H, int W, int Ht, int Wt, const int32_t* ysrc, const int32_t* xsrc,
+                             const float* lambdas_host, int L, uint8_t* out, evrep_stream_t stream);
+
 /* ------------------------------------------------- T3 / R1 / W1: output epilogues ----
  * evrep_nearest_resize: F.interpolate(mode='nearest') as used at generate_taf.py:222 --
  * out[c, Y, X] = in[c, ysrc[Y], xsrc[X]] with the legacy index maps (int32, device).

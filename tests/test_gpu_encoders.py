@@ -97,6 +97,60 @@ def test_sae_stream_state_bit_exact():
     assert close(g0, w0) and close(g1, w1)
 
 
+def _sae_window_list(t, bounds, nows):
+    return [(lo, hi, now, int(t[lo]) if hi > lo else 0, int(t[hi - 1]) if hi > lo else 0)
+            for (lo, hi), now in zip(bounds, nows)]
+
+
+def test_sae_whole_stream_matches_oracle_window_by_window():
+    """evrep_sae_stream: a first window of several seconds (cut into 250 ms bins inside), then
+    short ones, one of them empty; the frames and the carried state are bit-exact (float32-rounded
+    timestamps), the uint8 decays equal up to truncation flips."""
+    torch.set_num_threads(1)
+    (t, x, y, p), aos = stream(240, 304, 3_000_000, 6e5, 77)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    edges = [0, int(np.searchsorted(t, 2_400_000)), int(np.searchsorted(t, 2_450_000)), int(np.searchsorted(t, 2_450_000)),
+             int(np.searchsorted(t, 2_700_000)), len(t)]
+    bounds = list(zip(edges[:-1], edges[1:]))
+    nows = [2_400_000, 2_450_000, 2_500_000, 2_700_000, 3_000_001]
+    latest, mem = ops.sae_stream(ev, _sae_window_list(t, bounds, nows), (240, 304))
+    u8 = ops.sae_decay_u8_batch(latest, nows, LAMBDAS, (256, 320))
+    memory = None
+    for i, ((lo, hi), now) in enumerate(zip(bounds, nows)):
+        want, memory = oe.sae_surfaces(aos[lo:hi], (240, 304), LAMBDAS, memory, np.int64(now))
+        assert exact(latest[i], memory), i
+        want_u8 = oe.nearest_resize(want, (256, 320)).numpy().astype(np.uint8).reshape(3, 2, 256, 320)
+        diff = np.abs(u8[i].cpu().numpy().astype(np.int16) - want_u8.astype(np.int16))
+        assert diff.max() <= 1 and (diff != 0).mean() < 1e-3, i
+    assert exact(mem, memory)
+    # a second call continues from the returned state
+    (t2, x2, y2, p2), aos2 = stream(240, 304, 200_000, 6e5, 78)
+    t2 = (t2 + 3_000_001).astype(np.uint32)
+    aos2[:, 2] += 3_000_001
+    ev2 = ops.EventStream.from_numpy(t2, x2, y2, p2)
+    latest2, mem2 = ops.sae_stream(ev2, _sae_window_list(t2, [(0, len(t2))], [3_300_000]), (240, 304), mem)
+    _, want_mem2 = oe.sae_surfaces(aos2, (240, 304), LAMBDAS, memory, np.int64(3_300_000))
+    assert exact(latest2[0], want_mem2) and exact(mem2, want_mem2) and exact(mem, memory)      # input state untouched
+
+
+def test_sae_whole_stream_with_coordinate_maps_equals_per_window_path():
+    """1MP events on the 512x640 grid: the stream kernel and the per-window kernel agree bit for bit."""
+    (t, x, y, p), _ = stream(720, 1280, 400_000, 8e6, 79)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    maps = ops.make_coord_maps((720, 1280), (512, 640), DEV)
+    cuts = [0] + [int(np.searchsorted(t, v)) for v in (150_000, 200_000, 250_000, 400_000)]
+    nows = [150_000, 200_000, 250_000, 400_000]
+    bounds = list(zip(cuts[:-1], cuts[1:]))
+    latest, mem = ops.sae_stream(ev, _sae_window_list(t, bounds, nows), (512, 640), None, maps)
+    u8 = ops.sae_decay_u8_batch(latest, nows, LAMBDAS)
+    memory = None
+    for i, ((lo, hi), now) in enumerate(zip(bounds, nows)):
+        want_u8, memory = ops.sae_u8(ev.slice(lo, hi), (512, 640), (512, 640), LAMBDAS, memory, now, maps)
+        assert exact(latest[i], memory), i
+        assert exact(u8[i], want_u8), i
+    assert exact(mem, memory)
+
+
 @pytest.mark.parametrize("K", [5, 8])
 def test_event_volume_golden(golden, K):
     H, W = [int(v) for v in golden["shape"]]

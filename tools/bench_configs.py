@@ -76,8 +76,13 @@ def main():
     emit(config="2: Event Count Image driver (N=50k/100k/200k per label), GEN1 %gs" % args.gen1_seconds, events=n,
          labels=len(labels), ms=s * 1e3, labels_per_s=len(labels) / s, Mevents_per_s=n / s / 1e6)
     s = wall(lambda: [None for _ in g_sae.encode_recording(rec, labels, geom, "train")], reps=1)
-    emit(config="2: SAE driver (3 lambdas, memory carried), GEN1 %gs" % args.gen1_seconds, events=n, labels=len(labels),
-         ms=s * 1e3, labels_per_s=len(labels) / s, Mevents_per_s=n / s / 1e6)
+    emit(config="2: SAE driver, one call per label (3 lambdas, memory carried), GEN1 %gs" % args.gen1_seconds, events=n,
+         labels=len(labels), ms=s * 1e3, labels_per_s=len(labels) / s, Mevents_per_s=n / s / 1e6)
+    s = wall(lambda: [None for _ in g_sae.encode_recording_stream(rec, labels, geom)], reps=3)
+    algo = 9 * n + len(labels) * (8 * HW + 3 * 2 * 256 * 320)       # events + f32 frame + uint8 decays per label
+    emit(config="2: SAE driver, whole-stream kernel (256 labels per call), GEN1 %gs" % args.gen1_seconds, events=n,
+         labels=len(labels), ms=s * 1e3, labels_per_s=len(labels) / s, Mevents_per_s=n / s / 1e6,
+         frac_of_measured_peak=algo / s / 1e9 / peak)
     del rec
 
     # ---- 1MP (config 4): TAF K=4 next to the headline K=8, native-grid variant

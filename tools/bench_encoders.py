@@ -88,6 +88,19 @@ def main():
             _, mem = ops.sae(ev.slice(lo, hi), (H, W), lam, mem, t0 + 50000, maps)
     report("sae_3lambda_50ms_windows", timed(run_sae, args.iters), 9 * n + nw * (8 * 3 * HW + 8 * HW), n)
 
+    # whole-stream SAE: frames of latest timestamps (f32 [2,H,W] per window) + batched uint8 decays
+    sae_windows = [(lo, hi, t0 + 50000, int(t[lo]) if hi > lo else 0, int(t[hi - 1]) if hi > lo else 0) for lo, hi, t0 in windows]
+    frames = torch.empty((nw, 2, H, W), dtype=torch.float32, device=dev)
+    u8 = torch.empty((nw, 3, 2, H, W), dtype=torch.uint8, device=dev)
+    nows = [w[2] for w in sae_windows]
+
+    def run_sae_stream():
+        latest, _ = ops.sae_stream(ev, sae_windows, (H, W), None, maps, frames)
+        ops.sae_decay_u8_batch(latest, nows, lam, None, None, u8)
+    report("sae_stream_3lambda_50ms_windows_u8", timed(run_sae_stream, args.iters), 9 * n + nw * (8 * HW + 3 * 2 * HW), n)
+    report("sae_stream_frames_only", timed(lambda: ops.sae_stream(ev, sae_windows, (H, W), None, maps, frames), args.iters),
+           9 * n + nw * 8 * HW, n)
+
 
 if __name__ == "__main__":
     main()
