@@ -180,14 +180,14 @@ ev_tile_kernel(EvTileParams tp) {
             for (uint32_t i = tid; i < n4; i += kEvThreads) {
                 const uint4 lo = reinterpret_cast<uint4*>(acc)[i];
                 const uint32_t wr = acc_hi[i];
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lo.x | lo.y | lo.z | lo.w | wr) {               // most cells of a window are untouched
-                    reinterpret_cast<uint4*>(acc)[i] = make_uint4(0u, 0u, 0u, 0u);
-                    if (wr) acc_hi[i] = 0u;
+                reinterpret_cast<uint4*>(acc)[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (wr) acc_hi[i] = 0u;
+                if (c4 * 4u < npix) {
+                    float4 v;
                     v.x = value(lo.x, wr & 0xFFu); v.y = value(lo.y, (wr >> 8) & 0xFFu);
                     v.z = value(lo.z, (wr >> 16) & 0xFFu); v.w = value(lo.w, wr >> 24);
+                    __stcs(reinterpret_cast<float4*>(o + g), v);
                 }
-                if (c4 * 4u < npix) __stcs(reinterpret_cast<float4*>(o + g), v);
                 c4 += c4_step; g += g_step;
                 if (c4 >= p4) { c4 -= p4; g += g_wrap; }
             }
