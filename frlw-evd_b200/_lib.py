@@ -27,6 +27,16 @@ class EvWindow(ctypes.Structure):
     _fields_ = [("ev_begin", c_int64), ("ev_end", c_int64), ("t0", c_int64)]
 
 
+class CountSegment(ctypes.Structure):
+    """``evrep_count_segment`` (include/evrep.h)."""
+    _fields_ = [("ev_begin", c_int64), ("ev_end", c_int64)]
+
+
+class CountEmit(ctypes.Structure):
+    """``evrep_count_emit`` (include/evrep.h)."""
+    _fields_ = [("first_segment", c_int32), ("last_segment", c_int32)]
+
+
 class SaeWindow(ctypes.Structure):
     """``evrep_sae_window`` (include/evrep.h)."""
     _fields_ = [("ev_begin", c_int64), ("ev_end", c_int64), ("now", c_int64), ("t_first", c_int64), ("t_last", c_int64)]
@@ -60,6 +70,10 @@ SIGNATURES = {
     "evrep_event_volume_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "evrep_event_volume_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int64, c_int, c_int, c_int, P, P, c_int, c_int,
                                           P, c_int64, P, c_int64, P]),
+    "evrep_count_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
+    "evrep_count_stream": (c_int, [P, P, P, P, c_int64, P, c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int64,
+                                   P, c_int64, P]),
+    "evrep_count_lut_u8_batch": (c_int, [P, c_int64, c_int64, c_int, c_int, c_int, c_int, P, P, P, P]),
     "evrep_sae_stream_scratch_bytes": (c_int64, [c_int64, P, c_int, c_int, c_int]),
     "evrep_sae_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int, P, c_int64,
                                  P, c_int64, P]),

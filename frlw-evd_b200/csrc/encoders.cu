@@ -105,6 +105,34 @@ count_finalize_u8_kernel(const uint32_t* __restrict__ counts, int H, int W, int 
     }
 }
 
+// The same epilogue for the count frames of evrep_count_stream (uint8 counts saturated at 255),
+// all windows at once: out[w, c, Y, X] = u8(LUT[min(frames[w, c, ysrc[Y], xsrc[X]], 32)]).
+template <int kVec>      // output pixels per thread: 4 (one 32-bit store) when Wt % 4 == 0, else 1
+__global__ void __launch_bounds__(kBlock)
+count_lut_u8_batch_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int64_t n_windows, int H, int W,
+                          int Ht, int Wt, const int32_t* __restrict__ ysrc, const int32_t* __restrict__ xsrc,
+                          uint8_t* __restrict__ out) {
+    const int64_t per = (int64_t)2 * Ht * Wt / kVec, total = n_windows * per;
+    const int wq = Wt / kVec;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t w = i / per, j = i - w * per;
+        const int X0 = (int)(j % wq) * kVec;
+        const int64_t r = j / wq;
+        const int Y = (int)(r % Ht), c = (int)(r / Ht);
+        const int ys = ysrc ? ysrc[Y] : Y;
+        const uint8_t* row = frames + w * frame_stride + ((int64_t)c * H + ys) * W;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) {
+            const uint32_t n = row[xsrc ? xsrc[X0 + k] : X0 + k];
+            packed |= (uint32_t)(uint8_t)(int)c_count_lut[n < 32u ? n : 32u] << (8 * k);
+        }
+        if (kVec == 4) reinterpret_cast<uint32_t*>(out)[i] = packed;
+        else out[i] = (uint8_t)packed;
+    }
+}
+
 // ------------------------------------------------------------------ A1: SAE
 // Order-preserving float <-> u32 key (0 is reserved for "no event").
 __device__ __forceinline__ uint32_t float_key(float f) {
@@ -540,6 +568,24 @@ int evrep_count_image(const uint16_t* x, const uint16_t* y, const uint8_t* p, in
     int rc = evrep_count_accumulate(x, y, p, n, H, W, xmap, ymap, counts, stream);
     if (rc) return rc;
     return evrep_count_finalize(counts, H, W, out, 1, stream);
+}
+
+int evrep_count_lut_u8_batch(const uint8_t* frames, int64_t frame_stride, int64_t n_windows, int H, int W, int Ht, int Wt,
+                             const int32_t* ysrc, const int32_t* xsrc, uint8_t* out, evrep_stream_t stream) {
+    if (H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0 || n_windows < 0) return EVREP_ERR_ARG;
+    if (n_windows == 0) return EVREP_OK;
+    if (!frames || !out) return EVREP_ERR_ARG;
+    if ((!ysrc || !xsrc) && (Ht != H || Wt != W)) return EVREP_ERR_ARG;
+    int rc = ensure_count_lut();
+    if (rc) return rc;
+    if (Wt % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0)
+        count_lut_u8_batch_kernel<4><<<grid_for(n_windows * 2 * Ht * Wt / 4), kBlock, 0, as_stream(stream)>>>(
+            frames, frame_stride, n_windows, H, W, Ht, Wt, ysrc, xsrc, out);
+    else
+        count_lut_u8_batch_kernel<1><<<grid_for(n_windows * 2 * Ht * Wt), kBlock, 0, as_stream(stream)>>>(
+            frames, frame_stride, n_windows, H, W, Ht, Wt, ysrc, xsrc, out);
+    EVREP_LAUNCH_CHECK();
+    return EVREP_OK;
 }
 
 int evrep_count_images_u8(const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n, const int64_t* sizes_host,

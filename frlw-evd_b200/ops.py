@@ -424,6 +424,61 @@ def event_volume_stream(ev: EventStream, windows, tw: int, shape, K: int, maps=N
     return out
 
 
+def count_stream(ev: EventStream, windows, shape, maps=None):
+    """E1 + E2 for many windows in one call.  ``windows``: ``(ev_begin, ev_end)`` event ranges that
+    may nest and overlap (the driver's last-N windows of consecutive labels), in non-decreasing
+    order of ``ev_end``.  Returns u8 ``[n_windows, 2, H, W]`` event counts saturated at 255 (the
+    image value depends on ``min(count, 20)`` only); feed it to ``count_lut_u8_batch``."""
+    _need_cuda(ev.x)
+    H, W = shape
+    nw = len(windows)
+    frames = torch.zeros((nw, 2, H, W), dtype=torch.uint8, device=ev.device)
+    live = [i for i, (lo, hi) in enumerate(windows) if hi > lo]
+    if not live:
+        return frames
+    bounds = sorted({int(b) for i in live for b in windows[i]})
+    index = {b: k for k, b in enumerate(bounds)}
+    n_seg = len(bounds) - 1
+    seg = (_lib.CountSegment * n_seg)()
+    for k in range(n_seg):
+        seg[k] = _lib.CountSegment(bounds[k], bounds[k + 1])
+    order = sorted(live, key=lambda i: index[int(windows[i][1])])                 # stable: by last segment
+    emits = (_lib.CountEmit * len(order))()
+    for j, i in enumerate(order):
+        emits[j] = _lib.CountEmit(index[int(windows[i][0])], index[int(windows[i][1])] - 1)
+    out = frames if len(order) == nw and order == list(range(nw)) else torch.empty((len(order), 2, H, W), dtype=torch.uint8,
+                                                                                    device=ev.device)
+    need = _lib.load().evrep_count_stream_scratch_bytes(ev.n, n_seg, len(order), H, W)
+    if need < 0:
+        _lib.check(int(need), "evrep_count_stream_scratch_bytes")
+    buf = workspace("taf_stream", need, ev.device)
+    xm, ym = _maps(maps)
+    _lib.call("evrep_count_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+              ctypes.cast(seg, ctypes.c_void_p), n_seg, ctypes.cast(emits, ctypes.c_void_p), len(order), H, W, xm, ym,
+              maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W,
+              _ptr(out), 2 * H * W, _ptr(buf), buf.numel(), _stream(ev.device))
+    if out is not frames:
+        frames[torch.as_tensor(order, device=ev.device)] = out
+    return frames
+
+
+def count_lut_u8_batch(frames, target_shape=None, resize_maps=None, out=None):
+    """Value LUT, nearest resize and uint8 truncation of the count-image driver for all frames of a
+    ``count_stream`` result: u8 ``[n, 2, H, W]`` counts -> u8 ``[n, 2, Ht, Wt]`` images."""
+    _need_cuda(frames)
+    n, two, H, W = frames.shape
+    assert two == 2 and frames.is_contiguous()
+    Ht, Wt = target_shape if target_shape is not None else (H, W)
+    if (Ht, Wt) != (H, W) and resize_maps is None:
+        resize_maps = nearest_maps((H, W), (Ht, Wt), frames.device)
+    ys, xs = resize_maps if (Ht, Wt) != (H, W) else (None, None)
+    if out is None:
+        out = torch.empty((n, 2, Ht, Wt), dtype=torch.uint8, device=frames.device)
+    _lib.call("evrep_count_lut_u8_batch", _ptr(frames), 2 * H * W, n, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
+              _stream(frames.device))
+    return out
+
+
 def sae_stream(ev: EventStream, windows, shape, memory=None, maps=None, out=None):
     """A1 + A2 for every label of a recording in one call.  ``windows``: ordered, non-overlapping
     ``(ev_begin, ev_end, now, t_first, t_last)`` -- the events the driver hands to the encoder for

@@ -217,6 +217,39 @@ int evrep_event_volume_stream(const uint32_t* t, const uint16_t* x, const uint16
                               float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
                               evrep_stream_t stream);
 
+/* ------------------------------------------------- E1 + E2 over a whole stream -------
+ * generate_eventcountimage.py:130-182 for many labels in one call.  The driver's windows (the
+ * last N events before a label, several N per label) nest and overlap; the caller cuts the
+ * stream at every window boundary into consecutive segments [ev_begin, ev_end) and lists the
+ * windows as runs of segments [first_segment, last_segment], ordered by last_segment
+ * (first_segment == last_segment + 1 denotes an empty window).
+ * frames_out: u8 [n_emits][2,H,W] event counts per (polarity, pixel), saturated at 255 --
+ * frame i belongs to emits_host[i]; H*W and frame_stride must be multiples of 4.
+ * A window may span as many segments as fit the shared-memory ring (EVREP_ERR_RANGE otherwise;
+ * e.g. 39 segments at 512x640, 187 at 240x304).
+ * evrep_count_lut_u8_batch: value LUT (:32-41), nearest resize and uint8 truncation (:164,180)
+ * for all frames: out u8 [n_windows][2,Ht,Wt]. */
+typedef struct {
+    int64_t ev_begin;
+    int64_t ev_end;
+} evrep_count_segment;
+
+typedef struct {
+    int32_t first_segment;
+    int32_t last_segment;
+} evrep_count_emit;
+
+int64_t evrep_count_stream_scratch_bytes(int64_t n_events, int n_segments, int n_emits, int H, int W);
+int evrep_count_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+                       const evrep_count_segment* segments_host, int n_segments,
+                       const evrep_count_emit* emits_host, int n_emits, int H, int W,
+                       const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                       uint8_t* frames_out, int64_t frame_stride, void* scratch, int64_t scratch_bytes,
+                       evrep_stream_t stream);
+int evrep_count_lut_u8_batch(const uint8_t* frames, int64_t frame_stride, int64_t n_windows, int H, int W,
+                             int Ht, int Wt, const int32_t* ysrc, const int32_t* xsrc, uint8_t* out,
+                             evrep_stream_t stream);
+
 /* ------------------------------------------------- A1 + A2 over a whole stream -------
  * generate_surfaceofactiveevents.py:44-69 for every label of a recording in one call: window w
  * holds the events [ev_begin, ev_end) the driver (:147-175) hands to the encoder for label

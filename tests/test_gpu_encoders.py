@@ -97,6 +97,41 @@ def test_sae_stream_state_bit_exact():
     assert close(g0, w0) and close(g1, w1)
 
 
+def test_count_whole_stream_nested_overlapping_windows_bit_exact():
+    """evrep_count_stream + evrep_count_lut_u8_batch: the driver's last-N windows of consecutive
+    labels (nested inside a label, overlapping between labels, one empty, one reaching back to
+    event 0) equal the oracle's count image byte for byte, with and without the gen1 resize."""
+    (t, x, y, p), aos = stream(240, 304, 400_000, 1.5e6, 41)
+    # a hot pixel so that counts pass the saturation point of the LUT and of the 8-bit ring slots
+    x[::7], y[::7], p[::7] = 100, 50, 1
+    aos = torch.from_numpy(np.stack([x, y, t, p], 1).astype(np.float64))
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    ends = [0, 30_000, 90_000, 140_000, 200_000, 290_000, len(t)]
+    sizes = (20_000, 50_000, 120_000)
+    windows = [(max(e - n, 0), e) for e in ends for n in sizes]
+    frames = ops.count_stream(ev, windows, (240, 304))
+    native = ops.count_lut_u8_batch(frames)
+    resized = ops.count_lut_u8_batch(frames, (256, 320))
+    for i, (lo, hi) in enumerate(windows):
+        want = oe.count_image(aos[lo:hi], (240, 304))
+        assert exact(native[i], want.numpy().astype(np.uint8)), i
+        assert exact(resized[i], oe.nearest_resize(want, (256, 320)).numpy().astype(np.uint8)), i
+
+
+def test_count_whole_stream_with_coordinate_maps_equals_per_label_path():
+    (t, x, y, p), _ = stream(720, 1280, 300_000, 8e6, 42)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    maps = ops.make_coord_maps((720, 1280), (512, 640), DEV)
+    sizes = (400_000, 800_000, 1_200_000)
+    ends = [500_000, 900_000, 1_700_000, len(t)]
+    windows = [(max(e - n, 0), e) for e in ends for n in sizes]
+    got = ops.count_lut_u8_batch(ops.count_stream(ev, windows, (512, 640), maps))
+    for j, e in enumerate(ends):
+        lo = max(e - max(sizes), 0)
+        want = ops.count_images_u8(ev.slice(lo, e), sizes, (512, 640), (512, 640), maps)
+        assert exact(got[3 * j:3 * j + 3], want), j
+
+
 def _sae_window_list(t, bounds, nows):
     return [(lo, hi, now, int(t[lo]) if hi > lo else 0, int(t[hi - 1]) if hi > lo else 0)
             for (lo, hi), now in zip(bounds, nows)]

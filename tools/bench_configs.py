@@ -75,6 +75,11 @@ def main():
     s = wall(lambda: [None for _ in g_eci.encode_recording(rec, labels, geom, g_eci.windows_for("gen1"))], reps=1)
     emit(config="2: Event Count Image driver (N=50k/100k/200k per label), GEN1 %gs" % args.gen1_seconds, events=n,
          labels=len(labels), ms=s * 1e3, labels_per_s=len(labels) / s, Mevents_per_s=n / s / 1e6)
+    s = wall(lambda: [None for _ in g_eci.encode_recording_stream(rec, labels, geom, g_eci.windows_for("gen1"))], reps=3)
+    algo = 5 * n + len(labels) * 3 * (2 * HW + 2 * 256 * 320)       # events + uint8 count frame + uint8 image per window
+    emit(config="2: Event Count Image driver, whole-stream kernel (128 labels per call), GEN1 %gs" % args.gen1_seconds,
+         events=n, labels=len(labels), ms=s * 1e3, labels_per_s=len(labels) / s, Mevents_per_s=n / s / 1e6,
+         frac_of_measured_peak=algo / s / 1e9 / peak)
     s = wall(lambda: [None for _ in g_sae.encode_recording(rec, labels, geom, "train")], reps=1)
     emit(config="2: SAE driver, one call per label (3 lambdas, memory carried), GEN1 %gs" % args.gen1_seconds, events=n,
          labels=len(labels), ms=s * 1e3, labels_per_s=len(labels) / s, Mevents_per_s=n / s / 1e6)

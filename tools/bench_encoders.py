@@ -80,6 +80,22 @@ def main():
             ops.count_image(ev.slice(lo, hi), (H, W), maps)
     report("count_image_50ms_windows", timed(run_eci, args.iters), 5 * n + nw * 8 * HW, n)
 
+    # whole-stream count image: the gen4 driver's nested last-N windows (400k / 800k / 1.2M events) per 50 ms label
+    sizes = (400_000, 800_000, 1_200_000)
+    eci_windows = [(max(hi - s, 0), hi) for _, hi, _ in windows for s in sizes]
+    eci_out = torch.empty((len(eci_windows), 2, H, W), dtype=torch.uint8, device=dev)
+
+    def run_eci_stream():
+        ops.count_lut_u8_batch(ops.count_stream(ev, eci_windows, (H, W), maps), None, None, eci_out)
+    report("count_stream_last_400k_800k_1200k_per_label_u8", timed(run_eci_stream, args.iters),
+           5 * n + len(eci_windows) * 2 * 2 * HW, n, {"windows_encoded": len(eci_windows)})
+
+    def run_eci_labels():
+        for _, hi, _ in windows:
+            ops.count_images_u8(ev.slice(max(hi - max(sizes), 0), hi), sizes, (H, W), (H, W), maps)
+    report("count_per_label_last_400k_800k_1200k_u8", timed(run_eci_labels, args.iters),
+           5 * n + len(eci_windows) * 2 * HW, n, {"windows_encoded": len(eci_windows)})
+
     lam = [0.00001, 0.0000025, 0.000001]
 
     def run_sae():
