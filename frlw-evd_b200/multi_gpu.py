@@ -96,12 +96,12 @@ def encode_one(rep: str, dataset: str, mode: str, name: str, event_file: str, la
 
     if rep == "count_image":
         sizes = eci.windows_for(dataset)
-        for label, frames in eci.encode_recording(rec, labels, geom, sizes):
+        for label, frames in eci.encode_recording_stream(rec, labels, geom, sizes):
             for n, u8 in zip(sizes, frames):
                 put(u8, target_dir, "EventCountImage{0}".format(n), mode, name + "_" + str(label) + ".npy")
             windows += 1
     elif rep == "sae":
-        for label, u8 in sae.encode_recording(rec, labels, geom, mode):
+        for label, u8 in sae.encode_recording_stream(rec, labels, geom):
             for j, lam in enumerate(sae.LAMDAS):
                 put(u8[j], target_dir, "SurfaceOfActiveEvents{0}".format(lam), mode, name + "_" + str(label) + ".npy")
             windows += 1
