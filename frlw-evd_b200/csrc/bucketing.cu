@@ -88,11 +88,12 @@ struct ChunkOrigin {
 };
 
 __global__ void __launch_bounds__(256)
-taf_chunk_origin_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, ChunkOrigin* __restrict__ origins) {
+taf_chunk_origin_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, int chunk_events,
+                        ChunkOrigin* __restrict__ origins) {
     const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
     if (chunk >= n_chunks) return;
-    const int64_t c0 = ev_first + (int64_t)chunk * (kBucketThreads * kBucketPerThread);
-    const int64_t c1 = min(c0 + kBucketThreads * kBucketPerThread, ev_last);
+    const int64_t c0 = ev_first + (int64_t)chunk * chunk_events;
+    const int64_t c1 = min(c0 + chunk_events, ev_last);
     ChunkOrigin o;
     o.w0 = first_window(pl, c0);
     o.gb0 = 0; o.single = 0; o.pad = 0;
@@ -134,10 +135,17 @@ struct BucketSmem {
 //  scatter (kScatter = true):  the same histogram with ranks, a block scan, one global
 //          reservation per non-empty counter, then the chunk's records are ordered in shared
 //          memory so that each (tile, bin) run is written with consecutive addresses.
-template <bool kScatter>
+//  count + save (kMode = 2): the count pass that also stores every event's record and 16-bit
+//          histogram key, so that taf_scatter_saved_kernel need not classify the events again.
+enum : int { kModeCount = 0, kModeScatter = 1, kModeCountSave = 2 };
+constexpr uint32_t kKeyFar = 0xFFFEu, kKeyDropped = 0xFFFFu;     // saved keys that are not shared-memory counters
+
+template <int kMode>
 __global__ void __launch_bounds__(kBucketThreads, 2)
 taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, int lut_w, int lut_h,
                   const ChunkOrigin* __restrict__ origins, int vec_ok) {
+    constexpr bool kScatter = kMode == kModeScatter;
+    constexpr bool kSave = kMode == kModeCountSave;
     extern __shared__ __align__(16) unsigned char bsm[];
     const int nh = kLocalBins * pl.n_tiles;
     const BucketSmem lay(lut_w, lut_h, nh, kScatter);
@@ -170,7 +178,9 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
     for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const int64_t c0 = ev_first + (int64_t)chunk * (kBucketThreads * kBucketPerThread);
         const int64_t c1 = min(c0 + kBucketThreads * kBucketPerThread, ev_last);
-        const ChunkOrigin org = origins[chunk];            // same address for every thread: one broadcast load
+        // same address for every thread: one broadcast load.  In save mode the local-bin window is
+        // that of the enclosing scatter chunk, whose keys the scatter pass shares.
+        const ChunkOrigin org = origins[kSave ? chunk / kScatterChunks : chunk];
         __syncthreads();                                   // previous chunk is done with smem
         for (int i = threadIdx.x; i < nh; i += kBucketThreads) hist[i] = 0;
         const int gb0 = org.gb0;
@@ -217,7 +227,8 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
         __syncthreads();                                   // histogram is zeroed
         // per event: (smem counter << 12) | rank inside the chunk, or kNone when dropped
         constexpr uint32_t kNone = 0xFFFFFFFFu;
-        uint32_t slot[kBucketPerThread], rec[kBucketPerThread] = {};
+        uint32_t slot[kScatter ? kBucketPerThread : 1], rec[kBucketPerThread] = {};
+        uint32_t key16[kSave ? kBucketPerThread : 1];
 
         // count / rank one classified event
         auto deposit = [&](int k, uint32_t tile, int gbin) {
@@ -226,11 +237,13 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
                 const uint32_t key = lb * n_tiles + tile;
                 if (kScatter) slot[k] = (key << 12) | atomicAdd(&hist[key], 1u);
                 else atomicAdd(&hist[key], 1u);
+                if (kSave) key16[k] = key;
             } else {                          // unsorted input or a very sparse stream: go straight to global
                 uint32_t* cursor = pl.counts + (int64_t)tile * pl.TB + gbin;
                 if (kScatter)
                     pl.records[pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] + atomicAdd(cursor, 1u)] = rec[k];
                 else { atomicAdd(cursor, 1u); pl.bin_any[gbin] = 1u; }
+                if (kSave) key16[k] = kKeyFar;
             }
         };
         // grid pixel and polarity of event k; false when the event is to be dropped
@@ -249,34 +262,55 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
             const uint32_t start32 = (uint32_t)wi.start, zmax = (uint32_t)(wi.nbins - 1);
 #pragma unroll
             for (int k = 0; k < kBucketPerThread; ++k) {
-                slot[k] = kNone;
+                if (kScatter) slot[k] = kNone;
+                if (kSave) key16[k] = kKeyDropped;
                 uint32_t pix, pol;
-                if (!locate(k, pix, pol)) continue;
-                const uint32_t u = max(tt[k], start32) - start32;
-                const uint32_t z = min(pl.div_abin.div(u), zmax);
-                const uint32_t tile = tile_of(pix);
-                if (kScatter) rec[k] = (min(u - z * pl.abin, kDMax) << 14) | ((pix - tile * P) << 1) | pol;
-                deposit(k, tile, wi.binbase + (int)z);
+                if (locate(k, pix, pol)) {
+                    const uint32_t u = max(tt[k], start32) - start32;
+                    const uint32_t z = min(pl.div_abin.div(u), zmax);
+                    const uint32_t tile = tile_of(pix);
+                    if (kScatter || kSave) rec[k] = (min(u - z * pl.abin, kDMax) << 14) | ((pix - tile * P) << 1) | pol;
+                    deposit(k, tile, wi.binbase + (int)z);
+                }
+                if (kSave && vec_ok && (k & 3) == 3) {
+                    // events 4g .. 4g+3 of a thread are consecutive in the stream: one 16-byte and one 8-byte store
+                    const int64_t at = c0 - ev_first + ((int64_t)(k >> 2) * kBucketThreads + threadIdx.x) * 4;
+                    *reinterpret_cast<uint4*>(pl.saved_rec + at) = make_uint4(rec[k - 3], rec[k - 2], rec[k - 1], rec[k]);
+                    *reinterpret_cast<uint2*>(pl.saved_key + at) = make_uint2(key16[k - 3] | (key16[k - 2] << 16), key16[k - 1] | (key16[k] << 16));
+                }
+            }
+            if (kSave && !vec_ok) {
+#pragma unroll
+                for (int k = 0; k < kBucketPerThread; ++k) {
+                    const int64_t at = c0 - ev_first + k * kBucketThreads + threadIdx.x;
+                    pl.saved_rec[at] = rec[k]; pl.saved_key[at] = (uint16_t)key16[k];
+                }
             }
         } else {
 #pragma unroll
             for (int k = 0; k < kBucketPerThread; ++k) {
                 const int64_t i = c0 + k * kBucketThreads + threadIdx.x;
-                slot[k] = kNone;
+                if (kScatter) slot[k] = kNone;
                 if (i >= c1) continue;
+                bool in_window = true;
                 if (!single) {                  // chunk straddles a window boundary or a gap
                     while (w < pl.n_windows && i >= __ldg(pl.w_end + w)) ++w;
-                    if (w >= pl.n_windows) continue;
-                    wi = load_window(pl, w);
-                    if (i < wi.begin || wi.nbins <= 0) continue;
+                    in_window = w < pl.n_windows;
+                    if (in_window) {
+                        wi = load_window(pl, w);
+                        in_window = i >= wi.begin && wi.nbins > 0;
+                    }
                 }
-                uint32_t pix, pol;
-                if (!locate(k, pix, pol)) continue;
-                uint32_t z, d;
-                bin_of(pl, wi, tt[k], z, d);
-                const uint32_t tile = tile_of(pix);
-                rec[k] = (d << 14) | ((pix - tile * P) << 1) | pol;
-                deposit(k, tile, wi.binbase + (int)z);
+                uint32_t pix, pol, key = kKeyDropped;
+                if (in_window && locate(k, pix, pol)) {
+                    uint32_t z, d;
+                    bin_of(pl, wi, tt[k], z, d);
+                    const uint32_t tile = tile_of(pix);
+                    rec[k] = (d << 14) | ((pix - tile * P) << 1) | pol;
+                    deposit(k, tile, wi.binbase + (int)z);
+                    if (kSave) key = key16[k];
+                }
+                if (kSave) { pl.saved_rec[i - ev_first] = rec[k]; pl.saved_key[i - ev_first] = (uint16_t)key; }
             }
         }
         __syncthreads();
@@ -305,6 +339,118 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
             const uint32_t pos = loff[key] + (slot[k] & 0xFFFu);
             sorted[pos] = rec[k];
             skey[pos] = (uint16_t)key;
+        }
+        __syncthreads();
+        for (uint32_t pos = threadIdx.x; pos < n_valid; pos += kBucketThreads)
+            pl.records[gbase[skey[pos]] + pos] = sorted[pos];
+    }
+}
+
+// Tile, global bin and record of event i, from global memory only (the rare events whose bin lies
+// outside the local-bin window of their chunk: unsorted input, very sparse streams).
+__device__ __noinline__ bool classify_general(const SoA& ev, const StreamPlan& pl, int lut_w, int lut_h, int64_t i,
+                                              uint32_t& tile, int& gbin, uint32_t& rec) {
+    const int w = first_window(pl, i);
+    if (w >= pl.n_windows) return false;
+    const WinInfo wi = load_window(pl, w);
+    if (i < wi.begin || wi.nbins <= 0) return false;
+    uint32_t xm = ev.x[i], ym = ev.y[i];
+    const uint32_t pol = ev.p[i];
+    if (xm >= (uint32_t)lut_w || ym >= (uint32_t)lut_h || pol > 1u) return false;
+    if (ev.xmap) xm = ev.xmap[xm];
+    if (ev.ymap) ym = ev.ymap[ym];
+    if (xm >= (uint32_t)pl.W || ym >= (uint32_t)pl.H) return false;
+    uint32_t z, d;
+    bin_of(pl, wi, ev.t[i], z, d);
+    const uint32_t pix = ym * pl.W + xm;
+    tile = pl.div_P.div(pix);
+    gbin = wi.binbase + (int)z;
+    rec = (d << 14) | ((pix - tile * pl.P) << 1) | pol;
+    return true;
+}
+
+// Scatter pass over the records and keys saved by the count pass: no classification, 16 events per
+// thread (8192 per CTA, so the runs written per (tile, bin) are twice as long).  Ranks come from
+// returning shared-memory atomics, then block scan, one global reservation per non-empty counter,
+// records ordered in shared memory and written run by run.
+__global__ void __launch_bounds__(kBucketThreads, 2)
+taf_scatter_saved_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_super, int lut_w, int lut_h,
+                         const ChunkOrigin* __restrict__ origins) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    constexpr int kPer = kScatterPerThread;
+    constexpr int64_t kSuper = (int64_t)kBucketThreads * kPer;
+    const int nh = kLocalBins * pl.n_tiles;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(bsm);
+    uint32_t* loff = hist + nh;
+    uint32_t* gbase = loff + nh;
+    uint32_t* sorted = gbase + nh;
+    uint16_t* skey = reinterpret_cast<uint16_t*>(sorted + kSuper);
+    __shared__ uint32_t s_tmp[kBucketThreads / 32 + 1];
+    const uint32_t n_tiles = (uint32_t)pl.n_tiles;
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+    for (int sc = blockIdx.x; sc < n_super; sc += gridDim.x) {
+        const int64_t c0 = ev_first + (int64_t)sc * kSuper;
+        const int64_t c1 = min(c0 + kSuper, ev_last);
+        const int gb0 = origins[sc].gb0;
+        __syncthreads();                                   // previous chunk is done with smem
+        for (int i = threadIdx.x; i < nh; i += kBucketThreads) hist[i] = 0;
+        uint32_t rec[kPer], key[kPer];
+        if (c1 - c0 == kSuper) {
+#pragma unroll
+            for (int g = 0; g < kPer / 4; ++g) {
+                const int64_t at = c0 - ev_first + ((int64_t)g * kBucketThreads + threadIdx.x) * 4;
+                const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(pl.saved_rec + at));
+                const uint2 k4 = __ldg(reinterpret_cast<const uint2*>(pl.saved_key + at));
+                rec[4 * g + 0] = r4.x; rec[4 * g + 1] = r4.y; rec[4 * g + 2] = r4.z; rec[4 * g + 3] = r4.w;
+                key[4 * g + 0] = k4.x & 0xFFFFu; key[4 * g + 1] = k4.x >> 16; key[4 * g + 2] = k4.y & 0xFFFFu; key[4 * g + 3] = k4.y >> 16;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int64_t i = c0 + ((int64_t)(k >> 2) * kBucketThreads + threadIdx.x) * 4 + (k & 3);
+                key[k] = kKeyDropped; rec[k] = 0;
+                if (i < c1) { rec[k] = __ldg(pl.saved_rec + (i - ev_first)); key[k] = __ldg(pl.saved_key + (i - ev_first)); }
+            }
+        }
+        __syncthreads();                                   // histogram is zeroed
+        // key[k] becomes (counter << 13) | rank inside the chunk, kNone (dropped) or kFarMark
+        constexpr uint32_t kFarMark = 0xFFFFFFFEu;
+        bool any_far = false;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            if (key[k] < kKeyFar) key[k] = (key[k] << 13) | atomicAdd(&hist[key[k]], 1u);
+            else { any_far |= key[k] == kKeyFar; key[k] = key[k] == kKeyFar ? kFarMark : kNone; }
+        }
+        if (any_far) {                                     // rare: classify from the raw event, write straight to its run
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                if (key[k] != kFarMark) continue;
+                const int64_t i = c0 + ((int64_t)(k >> 2) * kBucketThreads + threadIdx.x) * 4 + (k & 3);
+                uint32_t tile, r;
+                int gbin;
+                if (classify_general(ev, pl, lut_w, lut_h, i, tile, gbin, r))
+                    pl.records[pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] +
+                               atomicAdd(pl.counts + (int64_t)tile * pl.TB + gbin, 1u)] = r;
+            }
+        }
+        __syncthreads();
+        const uint32_t n_valid = block_exclusive_scan(hist, loff, nh, s_tmp);
+        for (int i = threadIdx.x; i < nh; i += kBucketThreads) {
+            const uint32_t c = hist[i];
+            if (!c) continue;
+            const uint32_t lb = (uint32_t)i / n_tiles, tile = (uint32_t)i - lb * n_tiles;
+            const int gbin = gb0 + (int)lb;
+            gbase[i] = pl.tile_base[tile] + pl.off_rel[(int64_t)tile * (pl.TB + 1) + gbin] +
+                       atomicAdd(pl.counts + (int64_t)tile * pl.TB + gbin, c) - loff[i];
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            if (key[k] >= kFarMark) continue;
+            const uint32_t kk = key[k] >> 13;
+            const uint32_t pos = loff[kk] + (key[k] & 0x1FFFu);
+            sorted[pos] = rec[k];
+            skey[pos] = (uint16_t)kk;
         }
         __syncthreads();
         for (uint32_t pos = threadIdx.x; pos < n_valid; pos += kBucketThreads)
@@ -453,6 +599,12 @@ int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n
     o = align_up(o, 256);
     L.o_origins = o;  o += align_up((int64_t)sizeof(ChunkOrigin) * (n_events / (kBucketThreads * kBucketPerThread) + 2), 256);
     L.o_records = o;  o += align_up(4ll * (n_events + 4ll * L.n_tiles), 256);
+    {   // records / keys saved by the count pass, padded to whole scatter chunks
+        const int64_t super = (int64_t)kBucketThreads * kScatterPerThread;
+        const int64_t slots = (n_events / super + 2) * super;
+        L.o_savedrec = o; o += align_up(4ll * slots, 256);
+        L.o_savedkey = o; o += align_up(2ll * slots, 256);
+    }
     L.total = o;
     return EVREP_OK;
 }
@@ -542,6 +694,8 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
     pl.tile_base = reinterpret_cast<uint32_t*>(s + L.o_tilebase);
     pl.records = reinterpret_cast<uint32_t*>(s + L.o_records);
     pl.tile_bits = reinterpret_cast<uint32_t*>(s + L.o_tilebits);
+    pl.saved_rec = reinterpret_cast<uint32_t*>(s + L.o_savedrec);
+    pl.saved_key = reinterpret_cast<uint16_t*>(s + L.o_savedkey);
     pl.n_windows = n_windows; pl.n_batches = (int)batches.size(); pl.TB = (int)TB;
     pl.n_tiles = L.n_tiles; pl.P = L.P; pl.H = H; pl.W = W;
     pl.div_abin = FastDiv::make((uint32_t)abin);
@@ -570,15 +724,32 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
         const size_t smem_count = (size_t)BucketSmem(lut_w, lut_h, nh, false).total;
         const size_t smem_scatter = (size_t)BucketSmem(lut_w, lut_h, nh, true).total;
         if (smem_scatter > 100 * 1024) return EVREP_ERR_RANGE;          // two CTAs per SM
-        EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
-        EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
         SoA ev{t, x, y, p, xmap, ymap};
         ChunkOrigin* origins = reinterpret_cast<ChunkOrigin*>(s + L.o_origins);
-        if (grid > 0) {
-            taf_chunk_origin_kernel<<<(int)((n_chunks + 255) / 256), 256, 0, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, origins);
-            EVREP_LAUNCH_CHECK();
-            taf_bucket_kernel<false><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok);
-            EVREP_LAUNCH_CHECK();
+        // Default: the count pass saves every event's record and key and the scatter pass sorts those
+        // (no second classification).  EVREP_BUCKETING=reclassify selects the older scatter pass that
+        // reads and classifies the raw events again (kept for A/B runs).
+        const char* mode_env = getenv("EVREP_BUCKETING");
+        const bool reclassify = mode_env && strcmp(mode_env, "reclassify") == 0;
+        if (reclassify) {
+            EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<kModeCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+            EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<kModeScatter>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+            if (grid > 0) {
+                taf_chunk_origin_kernel<<<(int)((n_chunks + 255) / 256), 256, 0, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, (int)per_cta, origins);
+                EVREP_LAUNCH_CHECK();
+                taf_bucket_kernel<kModeCount><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok);
+                EVREP_LAUNCH_CHECK();
+            }
+        } else {
+            EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<kModeCountSave>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+            if (grid > 0) {
+                const int64_t n_super = (n_chunks + kScatterChunks - 1) / kScatterChunks;
+                taf_chunk_origin_kernel<<<(int)((n_super + 255) / 256), 256, 0, st>>>(ev, pl, ev_first, ev_last, (int)n_super,
+                                                                                    (int)(per_cta * kScatterChunks), origins);
+                EVREP_LAUNCH_CHECK();
+                taf_bucket_kernel<kModeCountSave><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok);
+                EVREP_LAUNCH_CHECK();
+            }
         }
         taf_scan_rows_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
         EVREP_LAUNCH_CHECK();
@@ -586,8 +757,15 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
         EVREP_LAUNCH_CHECK();
         taf_tile_bits_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
         EVREP_LAUNCH_CHECK();
-        if (grid > 0) {
-            taf_bucket_kernel<true><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok);
+        if (grid > 0 && reclassify) {
+            taf_bucket_kernel<kModeScatter><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok);
+            EVREP_LAUNCH_CHECK();
+        } else if (grid > 0) {
+            const int64_t n_super = (n_chunks + kScatterChunks - 1) / kScatterChunks;
+            const size_t smem_saved = (size_t)3 * nh * 4 + (size_t)kBucketThreads * kScatterPerThread * 6;
+            const int grid_saved = (int)(n_super < 2ll * sm_count() ? n_super : 2ll * sm_count());
+            EVREP_CUDA(cudaFuncSetAttribute(taf_scatter_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_saved));
+            taf_scatter_saved_kernel<<<grid_saved, kBucketThreads, smem_saved, st>>>(ev, pl, ev_first, ev_last, (int)n_super, lut_w, lut_h, origins);
             EVREP_LAUNCH_CHECK();
         }
     } else {

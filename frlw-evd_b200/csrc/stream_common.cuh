@@ -21,6 +21,8 @@ constexpr int kMaxTiles = 2048;         // kLocalBins * kMaxTiles counters fit t
 constexpr int kLocalBins = 4;           // bins covered by a bucketing CTA's smem histogram
 constexpr int kBucketThreads = 512;
 constexpr int kBucketPerThread = 8;     // 4096 events per bucketing CTA
+constexpr int kScatterPerThread = 16;   // 8192 saved records per CTA of the scatter pass
+constexpr int kScatterChunks = kScatterPerThread / kBucketPerThread;
 constexpr uint32_t kDMax = (1u << 18) - 1;
 constexpr float kTafInit = -6000.0f;    // generate_taf.py:207-209
 
@@ -64,6 +66,8 @@ struct StreamPlan {       // device pointers into the scratch buffer
     uint32_t* tile_base;  // [n_tiles+1] (multiples of 4 records: 16-byte aligned lists)
     uint32_t* records;    // [n_events + 4 n_tiles]
     uint32_t* tile_bits;  // [n_tiles][n_batches]: per batch, bit b = tile has records in bin b, bit 16+b = bin is non-empty anywhere
+    uint32_t* saved_rec;  // [events] record of every event as classified by the count pass (event order)
+    uint16_t* saved_key;  // [events] its shared-memory counter (local bin * n_tiles + tile), kKeyFar or kKeyDropped
     int n_windows, n_batches, TB, n_tiles, P, H, W;
     FastDiv div_abin, div_P;
     uint32_t abin;
@@ -191,7 +195,7 @@ struct BatchFeed {
 struct Layout {
     int P, n_tiles, slots;
     int64_t o_wbegin, o_wend, o_wstart, o_wnbins, o_wbinbase, o_batches, meta_bytes;
-    int64_t o_counts, o_binany, o_offrel, o_tiletotal, o_tilebase, o_tilebits, o_origins, o_records, total;
+    int64_t o_counts, o_binany, o_offrel, o_tiletotal, o_tilebase, o_tilebits, o_origins, o_records, o_savedrec, o_savedkey, total;
     int n_batches_max;
 };
 
