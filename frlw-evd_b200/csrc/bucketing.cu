@@ -45,10 +45,11 @@ __device__ __forceinline__ void bin_of(const StreamPlan& pl, const WinInfo& wi, 
     }
 }
 
-// Block-wide exclusive scan of n <= kBucketThreads * 16 shared-memory counters.
+// Block-wide exclusive scan of n shared-memory counters by kThreads threads.
 // Returns the total.  `tmp` holds one word per warp (+1).
+template <int kThreads = kBucketThreads>
 __device__ __forceinline__ uint32_t block_exclusive_scan(const uint32_t* in, uint32_t* out, int n, uint32_t* tmp) {
-    const int per = (n + kBucketThreads - 1) / kBucketThreads;
+    const int per = (n + kThreads - 1) / kThreads;
     const int lo = threadIdx.x * per, hi = min(lo + per, n);
     uint32_t mine = 0;
     for (int i = lo; i < hi; ++i) mine += in[i];
@@ -62,19 +63,19 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(const uint32_t* in, uin
     if (lane == 31) tmp[wid] = incl;
     __syncthreads();
     if (wid == 0) {
-        uint32_t w = lane < kBucketThreads / 32 ? tmp[lane] : 0u, wi = w;
+        uint32_t w = lane < kThreads / 32 ? tmp[lane] : 0u, wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
             if (lane >= o) wi += v;
         }
-        if (lane < kBucketThreads / 32) tmp[lane] = wi - w;
-        if (lane == kBucketThreads / 32 - 1) tmp[kBucketThreads / 32] = wi;
+        if (lane < kThreads / 32) tmp[lane] = wi - w;
+        if (lane == kThreads / 32 - 1) tmp[kThreads / 32] = wi;
     }
     __syncthreads();
     uint32_t run = tmp[wid] + incl - mine;
     for (int i = lo; i < hi; ++i) { const uint32_t c = in[i]; out[i] = run; run += c; }
-    const uint32_t total = tmp[kBucketThreads / 32];
+    const uint32_t total = tmp[kThreads / 32];
     __syncthreads();                     // `out` is complete (and `tmp` reusable) for every thread
     return total;
 }
@@ -373,19 +374,19 @@ __device__ __noinline__ bool classify_general(const SoA& ev, const StreamPlan& p
 // thread (8192 per CTA, so the runs written per (tile, bin) are twice as long).  Ranks come from
 // returning shared-memory atomics, then block scan, one global reservation per non-empty counter,
 // records ordered in shared memory and written run by run.
-__global__ void __launch_bounds__(kBucketThreads, 2)
+__global__ void __launch_bounds__(kSavedThreads, kSavedCtasPerSm)
 taf_scatter_saved_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_super, int lut_w, int lut_h,
                          const ChunkOrigin* __restrict__ origins) {
     extern __shared__ __align__(16) unsigned char bsm[];
     constexpr int kPer = kScatterPerThread;
-    constexpr int64_t kSuper = (int64_t)kBucketThreads * kPer;
+    constexpr int64_t kSuper = (int64_t)kSavedThreads * kPer;
     const int nh = kLocalBins * pl.n_tiles;
     uint32_t* hist = reinterpret_cast<uint32_t*>(bsm);
     uint32_t* loff = hist + nh;
     uint32_t* gbase = loff + nh;
     uint32_t* sorted = gbase + nh;
     uint16_t* skey = reinterpret_cast<uint16_t*>(sorted + kSuper);
-    __shared__ uint32_t s_tmp[kBucketThreads / 32 + 1];
+    __shared__ uint32_t s_tmp[kSavedThreads / 32 + 1];
     const uint32_t n_tiles = (uint32_t)pl.n_tiles;
     constexpr uint32_t kNone = 0xFFFFFFFFu;
 
@@ -394,12 +395,12 @@ taf_scatter_saved_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_las
         const int64_t c1 = min(c0 + kSuper, ev_last);
         const int gb0 = origins[sc].gb0;
         __syncthreads();                                   // previous chunk is done with smem
-        for (int i = threadIdx.x; i < nh; i += kBucketThreads) hist[i] = 0;
+        for (int i = threadIdx.x; i < nh; i += kSavedThreads) hist[i] = 0;
         uint32_t rec[kPer], key[kPer];
         if (c1 - c0 == kSuper) {
 #pragma unroll
             for (int g = 0; g < kPer / 4; ++g) {
-                const int64_t at = c0 - ev_first + ((int64_t)g * kBucketThreads + threadIdx.x) * 4;
+                const int64_t at = c0 - ev_first + ((int64_t)g * kSavedThreads + threadIdx.x) * 4;
                 const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(pl.saved_rec + at));
                 const uint2 k4 = __ldg(reinterpret_cast<const uint2*>(pl.saved_key + at));
                 rec[4 * g + 0] = r4.x; rec[4 * g + 1] = r4.y; rec[4 * g + 2] = r4.z; rec[4 * g + 3] = r4.w;
@@ -408,7 +409,7 @@ taf_scatter_saved_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_las
         } else {
 #pragma unroll
             for (int k = 0; k < kPer; ++k) {
-                const int64_t i = c0 + ((int64_t)(k >> 2) * kBucketThreads + threadIdx.x) * 4 + (k & 3);
+                const int64_t i = c0 + ((int64_t)(k >> 2) * kSavedThreads + threadIdx.x) * 4 + (k & 3);
                 key[k] = kKeyDropped; rec[k] = 0;
                 if (i < c1) { rec[k] = __ldg(pl.saved_rec + (i - ev_first)); key[k] = __ldg(pl.saved_key + (i - ev_first)); }
             }
@@ -426,7 +427,7 @@ taf_scatter_saved_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_las
 #pragma unroll
             for (int k = 0; k < kPer; ++k) {
                 if (key[k] != kFarMark) continue;
-                const int64_t i = c0 + ((int64_t)(k >> 2) * kBucketThreads + threadIdx.x) * 4 + (k & 3);
+                const int64_t i = c0 + ((int64_t)(k >> 2) * kSavedThreads + threadIdx.x) * 4 + (k & 3);
                 uint32_t tile, r;
                 int gbin;
                 if (classify_general(ev, pl, lut_w, lut_h, i, tile, gbin, r))
@@ -435,8 +436,8 @@ taf_scatter_saved_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_las
             }
         }
         __syncthreads();
-        const uint32_t n_valid = block_exclusive_scan(hist, loff, nh, s_tmp);
-        for (int i = threadIdx.x; i < nh; i += kBucketThreads) {
+        const uint32_t n_valid = block_exclusive_scan<kSavedThreads>(hist, loff, nh, s_tmp);
+        for (int i = threadIdx.x; i < nh; i += kSavedThreads) {
             const uint32_t c = hist[i];
             if (!c) continue;
             const uint32_t lb = (uint32_t)i / n_tiles, tile = (uint32_t)i - lb * n_tiles;
@@ -453,7 +454,7 @@ taf_scatter_saved_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_las
             skey[pos] = (uint16_t)kk;
         }
         __syncthreads();
-        for (uint32_t pos = threadIdx.x; pos < n_valid; pos += kBucketThreads)
+        for (uint32_t pos = threadIdx.x; pos < n_valid; pos += kSavedThreads)
             pl.records[gbase[skey[pos]] + pos] = sorted[pos];
     }
 }
@@ -600,7 +601,7 @@ int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n
     L.o_origins = o;  o += align_up((int64_t)sizeof(ChunkOrigin) * (n_events / (kBucketThreads * kBucketPerThread) + 2), 256);
     L.o_records = o;  o += align_up(4ll * (n_events + 4ll * L.n_tiles), 256);
     {   // records / keys saved by the count pass, padded to whole scatter chunks
-        const int64_t super = (int64_t)kBucketThreads * kScatterPerThread;
+        const int64_t super = (int64_t)kSavedThreads * kScatterPerThread;
         const int64_t slots = (n_events / super + 2) * super;
         L.o_savedrec = o; o += align_up(4ll * slots, 256);
         L.o_savedkey = o; o += align_up(2ll * slots, 256);
@@ -762,10 +763,11 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
             EVREP_LAUNCH_CHECK();
         } else if (grid > 0) {
             const int64_t n_super = (n_chunks + kScatterChunks - 1) / kScatterChunks;
-            const size_t smem_saved = (size_t)3 * nh * 4 + (size_t)kBucketThreads * kScatterPerThread * 6;
-            const int grid_saved = (int)(n_super < 2ll * sm_count() ? n_super : 2ll * sm_count());
+            const size_t smem_saved = (size_t)3 * nh * 4 + (size_t)kSavedThreads * kScatterPerThread * 6;
+            const int64_t resident = (int64_t)kSavedCtasPerSm * sm_count();
+            const int grid_saved = (int)(n_super < resident ? n_super : resident);
             EVREP_CUDA(cudaFuncSetAttribute(taf_scatter_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_saved));
-            taf_scatter_saved_kernel<<<grid_saved, kBucketThreads, smem_saved, st>>>(ev, pl, ev_first, ev_last, (int)n_super, lut_w, lut_h, origins);
+            taf_scatter_saved_kernel<<<grid_saved, kSavedThreads, smem_saved, st>>>(ev, pl, ev_first, ev_last, (int)n_super, lut_w, lut_h, origins);
             EVREP_LAUNCH_CHECK();
         }
     } else {

@@ -21,8 +21,11 @@ constexpr int kMaxTiles = 2048;         // kLocalBins * kMaxTiles counters fit t
 constexpr int kLocalBins = 4;           // bins covered by a bucketing CTA's smem histogram
 constexpr int kBucketThreads = 512;
 constexpr int kBucketPerThread = 8;     // 4096 events per bucketing CTA
-constexpr int kScatterPerThread = 16;   // 8192 saved records per CTA of the scatter pass
-constexpr int kScatterChunks = kScatterPerThread / kBucketPerThread;
+constexpr int kSavedThreads = 256;       // scatter pass over saved records: 256 threads x 16 records, 4 CTAs per SM
+constexpr int kSavedCtasPerSm = 4;
+constexpr int kScatterPerThread = 16;
+constexpr int kScatterChunks = kSavedThreads * kScatterPerThread / (kBucketThreads * kBucketPerThread);   // count chunks per scatter chunk
+static_assert(kScatterChunks >= 1 && kSavedThreads * kScatterPerThread % (kBucketThreads * kBucketPerThread) == 0, "scatter chunks are whole count chunks");
 constexpr uint32_t kDMax = (1u << 18) - 1;
 constexpr float kTafInit = -6000.0f;    // generate_taf.py:207-209
 
