@@ -192,6 +192,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     t, x, y, p = get_stream(1002 + rank, args.seconds, args.rate)
