@@ -192,7 +192,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # stdout carries the JSON line only
+        # stdout carries the JSON line only: NCCL honours NCCL_DEBUG_FILE above the VERSION level
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     t, x, y, p = get_stream(1002 + rank, args.seconds, args.rate)

@@ -150,7 +150,10 @@ def main(argv=None):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # keep stdout for the JSON summary
+        # stdout carries the JSON line only: NCCL honours NCCL_DEBUG_FILE above the VERSION level
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     recordings = list_recordings(args.raw_dir, args.label_dir)
     totals = run(recordings,
