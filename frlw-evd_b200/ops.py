@@ -424,30 +424,40 @@ def event_volume_stream(ev: EventStream, windows, tw: int, shape, K: int, maps=N
     return out
 
 
+def plan_count_segments(windows):
+    """Host-side plan of ``count_stream``: cut the event axis at every boundary of the non-empty
+    windows.  Returns ``(segments, order, emits)``: consecutive ``(ev_begin, ev_end)`` segments,
+    the indices of the non-empty windows sorted by their last segment, and for each of those (in
+    that order) the inclusive run ``(first_segment, last_segment)`` it covers."""
+    live = [i for i, (lo, hi) in enumerate(windows) if hi > lo]
+    bounds = sorted({int(b) for i in live for b in windows[i]})
+    index = {b: k for k, b in enumerate(bounds)}
+    segments = [(bounds[k], bounds[k + 1]) for k in range(len(bounds) - 1)]
+    order = sorted(live, key=lambda i: index[int(windows[i][1])])                 # stable: by last segment
+    emits = [(index[int(windows[i][0])], index[int(windows[i][1])] - 1) for i in order]
+    return segments, order, emits
+
+
 def count_stream(ev: EventStream, windows, shape, maps=None):
     """E1 + E2 for many windows in one call.  ``windows``: ``(ev_begin, ev_end)`` event ranges that
-    may nest and overlap (the driver's last-N windows of consecutive labels), in non-decreasing
-    order of ``ev_end``.  Returns u8 ``[n_windows, 2, H, W]`` event counts saturated at 255 (the
-    image value depends on ``min(count, 20)`` only); feed it to ``count_lut_u8_batch``."""
+    may nest and overlap (the driver's last-N windows of consecutive labels).  Returns u8
+    ``[n_windows, 2, H, W]`` event counts saturated at 255 (the image value depends on
+    ``min(count, 20)`` only); feed it to ``count_lut_u8_batch``."""
     _need_cuda(ev.x)
     H, W = shape
     nw = len(windows)
     frames = torch.zeros((nw, 2, H, W), dtype=torch.uint8, device=ev.device)
-    live = [i for i, (lo, hi) in enumerate(windows) if hi > lo]
-    if not live:
+    segments, order, runs = plan_count_segments(windows)
+    if not order:
         return frames
-    bounds = sorted({int(b) for i in live for b in windows[i]})
-    index = {b: k for k, b in enumerate(bounds)}
-    n_seg = len(bounds) - 1
+    n_seg = len(segments)
     seg = (_lib.CountSegment * n_seg)()
-    for k in range(n_seg):
-        seg[k] = _lib.CountSegment(bounds[k], bounds[k + 1])
-    order = sorted(live, key=lambda i: index[int(windows[i][1])])                 # stable: by last segment
+    for k, (lo, hi) in enumerate(segments):
+        seg[k] = _lib.CountSegment(lo, hi)
     emits = (_lib.CountEmit * len(order))()
-    for j, i in enumerate(order):
-        emits[j] = _lib.CountEmit(index[int(windows[i][0])], index[int(windows[i][1])] - 1)
-    out = frames if len(order) == nw and order == list(range(nw)) else torch.empty((len(order), 2, H, W), dtype=torch.uint8,
-                                                                                    device=ev.device)
+    for j, (first, last) in enumerate(runs):
+        emits[j] = _lib.CountEmit(first, last)
+    out = frames if order == list(range(nw)) else torch.empty((len(order), 2, H, W), dtype=torch.uint8, device=ev.device)
     need = _lib.load().evrep_count_stream_scratch_bytes(ev.n, n_seg, len(order), H, W)
     if need < 0:
         _lib.check(int(need), "evrep_count_stream_scratch_bytes")

@@ -100,3 +100,60 @@ def test_taf_window_plan_matches_oracle(recording, labels):
     got = [(w.fresh, w.start_time, w.end_time, w.start_count, w.end_count) for w in plan]
     assert got == [tuple(w) for w in want] and len(got) >= 5
     assert any(not w.fresh for w in plan) and sum(w.fresh for w in plan) >= 1
+
+
+def test_count_stream_segment_plan():
+    """``ops.plan_count_segments``: nested and overlapping windows become runs of consecutive
+    segments; empty windows are left out; the emission order is by last segment."""
+    from frlw_evd_b200 import ops
+    windows = [(0, 0), (10, 30), (0, 30), (25, 60), (40, 60), (60, 60), (5, 100)]
+    segments, order, runs = ops.plan_count_segments(windows)
+    assert segments == [(0, 5), (5, 10), (10, 25), (25, 30), (30, 40), (40, 60), (60, 100)]
+    assert all(a[1] == b[0] for a, b in zip(segments, segments[1:]))
+    assert order == [1, 2, 3, 4, 6]
+    for i, (first, last) in zip(order, runs):
+        assert segments[first][0] == windows[i][0] and segments[last][1] == windows[i][1]
+    assert [last for _, last in runs] == sorted(last for _, last in runs)
+    assert ops.plan_count_segments([(3, 3)]) == ([], [], [])
+
+
+def test_sae_and_count_stream_drivers_plan_like_the_oracle_drivers(tmp_path):
+    """The window lists of the whole-stream SAE driver equal the event ranges the oracle driver
+    encodes label by label."""
+    import numpy as np
+    from frlw_evd_b200 import generate_surfaceofactiveevents as g_sae, synth
+    from frlw_evd_b200.io import PSEELoader
+    from oracle.psee_io import Loader
+    t, x, y, p = synth.make_stream(240, 304, 7_000_000, 2e4, 12)
+    path = str(tmp_path / "rec_td.dat")
+    synth.write_dat(path, t, x, y, p, 240, 304)
+    labels = [300_000, 350_000, 5_900_000, 6_000_000, 6_050_000, 6_999_000, 8_000_000]
+    plan = g_sae.plan_windows(PSEELoader(path), labels)
+    loader, want = Loader(path), []
+    t_upper, c_upper = -100000000, 0
+    for label in labels:                       # oracle/drivers.py:run_sae, largest sub-window
+        end_count = loader.seek_time(label)
+        if end_count is None:
+            continue
+        start_time = label - 5000000
+        start_count = loader.seek_time(0 if start_time < 0 else start_time)
+        if start_count is None or start_time < 0:
+            start_count = 0
+        if start_time <= t_upper:
+            start_count = c_upper
+        t_upper, c_upper = label, end_count
+        lo = start_count + int(np.searchsorted(t[start_count:end_count], label - 5541263, side="right"))
+        want.append((label, lo, end_count))
+    assert plan == want and len(plan) >= 5
+
+
+def test_bind_to_device_is_best_effort():
+    """``affinity.bind_to_device`` reports what it did and never raises (no NVML on the CPU box)."""
+    import os
+    from frlw_evd_b200.affinity import bind_to_device
+    before = os.sched_getaffinity(0)
+    info = bind_to_device(0)
+    assert set(info) >= {"bound", "cpus", "how"}
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
