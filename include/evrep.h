@@ -281,6 +281,26 @@ int evrep_sae_decay_u8_batch(const float* latest, int64_t latest_stride, const f
                              int H, int W, int Ht, int Wt, const int32_t* ysrc, const int32_t* xsrc,
                              const float* lambdas_host, int L, uint8_t* out, evrep_stream_t stream);
 
+/* ------------------------------------------------- training-time read path (8f) -----
+ * data/dataset.py:219-234 for a batch of samples already in device memory.  Sample s is the
+ * raw uint8 content of its file(s), [C, Hs, Ws] at files + s * file_stride (for TAF K = 8 the
+ * bins4 file followed by the bins8 file, :294-308).  One pass does: float conversion, nearest
+ * resize to (up_h, up_w) = int(input_img_size * sr) (F.interpolate legacy index rule), / 255,
+ * crop img[:, -cy : Hin - cy, -cx : Win - cx] (cy, cx <= 0 as drawn at :153-161) and the
+ * horizontal flip.  out: f32 [n, C, Hin, Win] (the reference returns [C, Hin, Win, 1, 1] per
+ * sample).  aug: DEVICE array of n descriptors.  The crop must lie inside the resized image:
+ * Hin - cy <= up_h and Win - cx <= up_w. */
+typedef struct {
+    int32_t up_h;
+    int32_t up_w;
+    int32_t cy;
+    int32_t cx;
+    int32_t flip;
+} evrep_sample_aug;
+
+int evrep_load_samples(const uint8_t* files, int64_t file_stride, int n, int C, int Hs, int Ws,
+                       const evrep_sample_aug* aug, int Hin, int Win, float* out, evrep_stream_t stream);
+
 /* ------------------------------------------------- T3 / R1 / W1: output epilogues ----
  * evrep_nearest_resize: F.interpolate(mode='nearest') as used at generate_taf.py:222 --
  * out[c, Y, X] = in[c, ysrc[Y], xsrc[X]] with the legacy index maps (int32, device).

@@ -175,11 +175,88 @@ def driver_golden():
     return result
 
 
+# (img_size, input_img_size, sr, crop fractions in [0,1) of the admissible range, flip)
+DATASET_CASES = [((32, 40), (32, 40), 1.0, 0.0, 0.0, False),
+                 ((32, 40), (32, 40), 1.0, 0.0, 0.0, True),
+                 ((32, 40), (32, 40), 1.3, 0.35, 0.8, False),
+                 ((32, 40), (32, 40), 1.4999, 0.999, 0.01, True),
+                 ((32, 40), (48, 56), 1.17, 0.5, 0.5, True),
+                 ((24, 36), (32, 40), 1.0, 0.0, 0.0, False)]
+
+
+def dataset_golden():
+    """Run the unmodified ``data/dataset.py:propheseeTafDataset.__getitem__`` on a tiny on-disk
+    dataset with the random draws of its augmentation pinned, and record inputs and outputs."""
+    import random
+    import sys
+    import types
+    import numpy.lib.format as nf
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    if not hasattr(nf, "_read_array_header"):                       # numpy-2 shim (SURVEY 8c)
+        nf._read_array_header = lambda fp, version: (nf.read_array_header_1_0(fp) if version == (1, 0)
+                                                     else nf.read_array_header_2_0(fp))
+    import importlib
+    ds_mod = importlib.import_module("data.dataset")
+    out = {}
+    K = 8
+    saved = (random.random, random.uniform)
+    try:
+        for i, (img_size, in_size, sr, fx, fy, flip) in enumerate(DATASET_CASES):
+            with tempfile.TemporaryDirectory() as tmp:
+                label_dir, data_dir = os.path.join(tmp, "labels"), os.path.join(tmp, "taf")
+                os.makedirs(os.path.join(label_dir, "train"))
+                t_label = 100000 + 50000 * i
+                # boxes that survive every crop, so that the augmentation loop ends at its first draw
+                boxes = np.zeros(2, dtype=synth.BBOX_DTYPE)
+                boxes["t"] = t_label
+                boxes["x"], boxes["y"], boxes["w"], boxes["h"] = 100.0, 80.0, 120.0, 90.0
+                np.save(os.path.join(label_dir, "train", "rec_bbox.npy"), boxes)
+                rng = np.random.default_rng(700 + i)
+                files = {}
+                for sub in ("bins4", "bins8"):
+                    os.makedirs(os.path.join(data_dir, "train", sub))
+                    files[sub] = rng.integers(0, 256, (K, img_size[0], img_size[1]), dtype=np.uint8)
+                    files[sub].tofile(os.path.join(data_dir, "train", sub, "rec_%d.npy" % t_label))
+                Hin, Win = in_size
+                lo_x, lo_y = int(Win - sr * Win), int(Hin - sr * Hin)
+                cx_draw, cy_draw = lo_x * (1.0 - fx), lo_y * (1.0 - fy)      # a point of uniform(lo, 0)
+                draws = {"random": [0.1 if sr > 1.0 else 0.9, 0.1 if flip else 0.9], "uniform": [sr, cx_draw, cy_draw], "r": 0, "u": 0}
+
+                def fake_random():
+                    v = draws["random"][draws["r"] % 2]
+                    draws["r"] += 1
+                    return v
+
+                def fake_uniform(a, b):
+                    v = draws["uniform"][draws["u"] % 3]
+                    draws["u"] += 1
+                    assert min(a, b) <= v <= max(a, b), (a, b, v)
+                    return v
+                random.random, random.uniform = fake_random, fake_uniform
+                ds = ds_mod.propheseeTafDataset(label_dir, data_dir, dataset="gen1", input_img_size=list(in_size),
+                                                img_size=list(img_size), event_volume_bins=K, mode="train", augment=True)
+                img, _labels, _name, _t = ds[0]
+                random.random, random.uniform = saved
+                assert draws["r"] == 2 and draws["u"] == (3 if sr > 1.0 else 0), draws      # one pass of the loop
+                out["ds%d_bins4" % i], out["ds%d_bins8" % i] = files["bins4"], files["bins8"]
+                out["ds%d_params" % i] = np.array([img_size[0], img_size[1], Hin, Win, int(cx_draw) if sr > 1.0 else 0,
+                                                   int(cy_draw) if sr > 1.0 else 0, int(flip)], dtype=np.int64)
+                out["ds%d_sr" % i] = np.array([sr], dtype=np.float64)
+                out["ds%d_out" % i] = np.ascontiguousarray(img).astype(np.float32)
+    finally:
+        random.random, random.uniform = saved
+    np.savez_compressed(os.path.join(GOLDEN, "dataset_read.npz"), **out)
+    return out
+
+
 def main():
     assert rh.available(), "reference not mounted at " + rh.REFERENCE_ROOT
     os.makedirs(GOLDEN, exist_ok=True)
     enc = encoder_golden()
     drv = driver_golden()
+    dsg = dataset_golden()
+    print("dataset_read.npz:", len(dsg), "arrays")
     print("encoders_small.npz:", len(enc), "arrays;", "drivers_digest.json:",
           sum(len(v) for v in drv.values()), "files")
 

@@ -34,3 +34,10 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "encoders_small.npz"))
+
+
+@pytest.fixture(scope="session")
+def dataset_golden():
+    """Inputs / outputs of the reference's own ``propheseeTafDataset.__getitem__`` (oracle/make_golden.py)."""
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "dataset_read.npz"))

@@ -96,6 +96,30 @@ def main():
     report("count_per_label_last_400k_800k_1200k_u8", timed(run_eci_labels, args.iters),
            5 * n + len(eci_windows) * 2 * HW, n, {"windows_encoded": len(eci_windows)})
 
+    # training-time read path (8f rank 2): a batch of 32 gen4 TAF samples, uint8 [16,512,640] each, augmented
+    from frlw_evd_b200.data import dataset_gpu as dg
+    import time as _time
+    from oracle import dataset_read as dr
+    rng = np.random.default_rng(5)
+    vols_host = rng.integers(0, 256, (32, 16, H, W), dtype=np.uint8)
+    vols = torch.from_numpy(vols_host).to(dev)
+    aug = []
+    for i in range(32):
+        sr = 1.0 if i % 2 == 0 else float(rng.uniform(1.0, 1.5))
+        cx = int(rng.uniform(int(W - sr * W), 0)) if sr > 1.0 else 0
+        cy = int(rng.uniform(int(H - sr * H), 0)) if sr > 1.0 else 0
+        aug.append((sr, cx, cy, bool(i & 2)))
+    batch_out = torch.empty((32, 16, H, W), dtype=torch.float32, device=dev)
+    ms = timed(lambda: dg.augment_batch(vols, (H, W), aug, batch_out), args.iters)
+    tick = _time.perf_counter()
+    for i in range(4):
+        dr.augment_sample(vols_host[i].astype(np.float32), (H, W), *aug[i])
+    cpu_ms = (_time.perf_counter() - tick) / 4 * 1e3
+    print(json.dumps({"encoder": "dataset_read_batch32_gen4_taf", "ms": ms, "samples_per_s": 32 / ms * 1e3,
+                      "algorithmic_bytes": 32 * 16 * HW * 5, "achieved_GBs": 32 * 16 * HW * 5 / ms / 1e6,
+                      "frac_of_measured_peak": 32 * 16 * HW * 5 / ms / 1e6 / peak,
+                      "cpu_oracle_ms_per_sample": cpu_ms, "cpu_threads": torch.get_num_threads()}))
+
     lam = [0.00001, 0.0000025, 0.000001]
 
     def run_sae():
