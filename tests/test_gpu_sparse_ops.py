@@ -57,3 +57,29 @@ def test_event_queue_tensor(golden):
     assert got.dtype == np.float64 and got.shape == golden["q_out"].shape
     assert np.allclose(got, golden["q_out"], rtol=1e-5, atol=1e-5)
     assert np.array_equal(got[1], golden["q_out"][1]) and np.array_equal(got[0, :4], golden["q_out"][0, :4])
+
+
+def test_fetcher_streams_agile_event_volume_like_the_oracle():
+    """``data/fetcher.py`` twin driving ``sparse_ops.generate_agile_event_volume_cuda`` on the
+    device (events uploaded once, one index range per step) against the oracle encoder fed with
+    the host-side boolean masks of the reference fetcher (``data/fetcher.py:35-55``)."""
+    from frlw_evd_b200.data import fetcher as ft
+    from oracle import encoders as oe
+    rng = np.random.default_rng(8)
+    n, B, H, W = 60000, 2, 30, 40
+    ev = np.stack([rng.integers(0, B, n), rng.integers(0, W, n), rng.integers(0, H, n),
+                   np.sort(rng.integers(0, 100000, n)), rng.integers(0, 2, n)], 1).astype(np.float64)
+    labels = torch.tensor([[b, 1, 2, 3, 4, 0, 1000.0 * k] for b in range(B) for k in range(0, 200, 5)], dtype=torch.float64)
+    timestamps = np.array([[0, 100000], [0, 100000]], dtype=np.int64)
+    f = ft.fetcherVal(ev, (H, W), labels, timestamps, ["a", "b"], 50000, 5, 10000, so.generate_agile_event_volume_cuda)
+    it, memory, steps = 0, None, 0
+    while not f.finish:
+        volume, _labels, _ts, _names, _secs = f.fetch()
+        if it == 0:
+            sel, it = ev[ev[:, 3] < 50000], 50000
+        else:
+            sel, it = ev[(ev[:, 3] < it + 10000) & (ev[:, 3] >= it)], it + 10000
+        want, memory = oe.sparse_agile_event_volume(torch.from_numpy(sel), B, (H, W), it, memory, 50000, 5, 10000)
+        assert f.iter == it and close(volume, want.numpy()), steps
+        steps += 1
+    assert steps == 6

@@ -157,3 +157,45 @@ def test_bind_to_device_is_best_effort():
     if not info["bound"]:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+@pytest.mark.reference
+def test_fetcher_steps_like_the_reference_fetcher():
+    """``data/fetcher.py`` twin against the unmodified reference class on CPU: the same events
+    reach ``to_volume`` at every step, with the same ``iter`` / window arguments, and the labels,
+    timestamps and finish flag agree (``data/fetcher.py:35-62``)."""
+    import importlib.util
+    import numpy as np
+    import torch
+    from oracle import ref_harness as rh
+    from frlw_evd_b200.data import fetcher as mine
+    spec = importlib.util.spec_from_file_location("ref_fetcher", rh.REFERENCE_ROOT + "/data/fetcher.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(2)
+    n, B = 5000, 2
+    ev = np.stack([rng.integers(0, B, n), rng.integers(0, 40, n), rng.integers(0, 30, n),
+                   np.sort(rng.integers(0, 90000, n)), rng.integers(0, 2, n)], 1).astype(np.float64)
+    labels = torch.tensor([[b, 1, 2, 3, 4, 0, 1000.0 * k + 50000] for b in range(B) for k in range(0, 45, 5)], dtype=torch.float64)
+    timestamps = np.array([[1000, 91000], [2000, 92000]], dtype=np.int64)
+    seen = {"ref": [], "mine": []}
+
+    def recorder(tag):
+        def to_volume(events, batch, shape, it, memory, window, bins, abin):
+            seen[tag].append((np.asarray(events.cpu()), batch, tuple(shape), it, memory, window, bins, abin))
+            return torch.zeros(1), len(seen[tag])
+        return to_volume
+    with rh._cpu_cuda_shims():
+        a = ref.fetcherTrain(ev, (30, 40), labels, timestamps, ["x", "y"], 50000, 5, 10000, recorder("ref"))
+        b = mine.fetcherTrain(ev, (30, 40), labels, timestamps, ["x", "y"], 50000, 5, 10000, recorder("mine"), device="cpu")
+        for _ in range(5):
+            ra, rb = a.fetch(), b.fetch()
+            assert (ra[1] is None) == (rb[1] is None)
+            if ra[1] is not None:
+                assert torch.equal(ra[1], rb[1])
+            assert np.array_equal(ra[2], rb[2]) and ra[3] == rb[3] and a.finish == b.finish and a.iter == b.iter
+            if a.finish:
+                break
+    assert len(seen["ref"]) == len(seen["mine"]) >= 4
+    for x, y in zip(seen["ref"], seen["mine"]):
+        assert np.array_equal(x[0], y[0]) and x[1:] == y[1:]
