@@ -255,3 +255,28 @@ def test_epilogues():
     # uint8 truncation of a float: allow the 1-LSB flips of log1pf vs the CPU kernel
     diff = np.abs(got.astype(int) - ref.astype(int))
     assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+
+
+def test_stream_encoders_edge_cases():
+    """No windows, windows without events, events that all fall off the grid."""
+    (t, x, y, p), aos = stream(240, 304, 100_000, 5e5, 91)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    n = len(t)
+    # no windows at all
+    assert ops.count_stream(ev, [], (240, 304)).shape == (0, 2, 240, 304)
+    latest, mem = ops.sae_stream(ev, [], (240, 304))
+    assert latest.shape == (0, 2, 240, 304)
+    # only empty windows
+    frames = ops.count_stream(ev, [(5, 5), (n, n)], (240, 304))
+    assert int(frames.sum()) == 0
+    latest, mem = ops.sae_stream(ev, [(7, 7, 60_000, 0, 0)], (240, 304))
+    want, want_mem = oe.sae_surfaces(aos[7:7], (240, 304), LAMBDAS, None, np.int64(60_000))
+    assert exact(latest[0], want_mem) and exact(mem, want_mem)
+    # every event outside the grid: dropped, like the per-window kernels
+    far = ops.EventStream.from_numpy(t, (x + 400).astype(np.uint16), y, p)
+    assert int(ops.count_stream(far, [(0, n)], (240, 304)).sum()) == 0
+    latest, _ = ops.sae_stream(far, [(0, n, 100_000, int(t[0]), int(t[-1]))], (240, 304))
+    floor = np.float32(np.float32(100_000.0) - np.float32(5_000_000.0))
+    assert np.all(latest.cpu().numpy() == floor)
+    vol = ops.event_volume_stream(far, [(0, n, 0)], 100_000, (240, 304), 5)
+    assert float(vol.abs().sum()) == 0.0
