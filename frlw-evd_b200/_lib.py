@@ -78,6 +78,8 @@ SIGNATURES = {
     "evrep_sae_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int, P, c_int64,
                                  P, c_int64, P]),
     "evrep_sae_decay_u8_batch": (c_int, [P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P]),
+    "evrep_timesurface_scratch_bytes": (c_int64, [c_int, c_int]),
+    "evrep_timesurface": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P]),
     "evrep_load_samples": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, c_int, c_int, P, P]),
     "evrep_nearest_resize": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "evrep_quantize_u8": (c_int, [P, c_int64, c_int, P, P]),

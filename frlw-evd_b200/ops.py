@@ -424,6 +424,20 @@ def event_volume_stream(ev: EventStream, windows, tw: int, shape, K: int, maps=N
     return out
 
 
+def timesurface(ev: EventStream, shape):
+    """Time-surface pair of ``generate_opticalflow.py:72-92`` on a SoA slice: ``(f64 [H,W] last
+    timestamp older than newest - 50000, f64 [H,W] last timestamp)``, shifted, scaled and clamped
+    like the reference."""
+    _need_cuda(ev.t)
+    H, W = shape
+    out_old = torch.empty((H, W), dtype=torch.float64, device=ev.device)
+    out_all = torch.empty((H, W), dtype=torch.float64, device=ev.device)
+    buf = scratch("timesurface", _lib.load().evrep_timesurface_scratch_bytes(H, W), ev.device)
+    _lib.call("evrep_timesurface", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), ev.n, H, W, _ptr(buf), _ptr(out_old), _ptr(out_all),
+              _stream(ev.device))
+    return out_old, out_all
+
+
 def plan_count_segments(windows):
     """Host-side plan of ``count_stream``: cut the event axis at every boundary of the non-empty
     windows.  Returns ``(segments, order, emits)``: consecutive ``(ev_begin, ev_end)`` segments,

@@ -281,6 +281,17 @@ int evrep_sae_decay_u8_batch(const float* latest, int64_t latest_stride, const f
                              int H, int W, int Ht, int Wt, const int32_t* ysrc, const int32_t* xsrc,
                              const float* lambdas_host, int L, uint8_t* out, evrep_stream_t stream);
 
+/* ------------------------------------------------- time-surface pair (8f) ------------
+ * generate_opticalflow.py:72-92 (generate_timesurface with zero-initialised volumes): out_all =
+ * last timestamp per pixel, out_old = last timestamp older than (newest - 50000), both shifted to
+ * the oldest timestamp of the call, scaled by 255 / (newest - 50000 - oldest) in float64 and
+ * clamped below at 0.  out_*: f64 [H,W].  Events outside the grid are dropped (the driver filters
+ * them, :176); polarity is not used.  scratch: evrep_timesurface_scratch_bytes bytes, zero on
+ * entry, left zeroed. */
+int64_t evrep_timesurface_scratch_bytes(int H, int W);
+int evrep_timesurface(const uint32_t* t, const uint16_t* x, const uint16_t* y, int64_t n, int H, int W,
+                      void* scratch, double* out_old, double* out_all, evrep_stream_t stream);
+
 /* ------------------------------------------------- training-time read path (8f) -----
  * data/dataset.py:219-234 for a batch of samples already in device memory.  Sample s is the
  * raw uint8 content of its file(s), [C, Hs, Ws] at files + s * file_stride (for TAF K = 8 the

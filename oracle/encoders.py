@@ -296,3 +296,28 @@ def event_queue_tensor(events, queue_length, B, H, W, start_times, event_window_
     out[0, Q - 1, pos] = total[pos]
     # plane 1 keeps -1 in slot Q-1 for pushed cells too (ecd_now is never updated)
     return out.reshape(2, Q, 2, B, H, W).astype(np.float64)
+
+
+# --------------------------------------------------------------------------- 8f rank 4
+def timesurface_pair(events, shape):
+    """Time-surface pair of ``generate_opticalflow.py:72-92`` (``generate_timesurface`` with
+    zero-initialised ``volume1`` / ``volume2``): float64 ``[N,4]`` (x, y, t, p) in array order ->
+    two float64 ``[H,W]`` surfaces.  ``volume2`` holds the last timestamp per pixel, ``volume1`` the
+    last one older than ``end - 50000``; both are shifted to the window start, scaled by
+    ``255 / (end - 50000 - start)`` and clamped below at 0.  Polarity is ignored."""
+    H, W = shape
+    ev = np.asarray(events, dtype=np.float64)
+    v1, v2 = np.zeros((H, W)), np.zeros((H, W))
+    if len(ev) > 0:
+        end, start = ev[:, 2].max(), ev[:, 2].min()
+        xs, ys, ts = ev[:, 0].astype(np.int64), ev[:, 1].astype(np.int64), ev[:, 2]
+        old = ts < end - 50000
+        v1[ys[old], xs[old]] = ts[old]           # fancy assignment writes in array order: last event wins
+        v2[ys, xs] = ts
+        v1 = v1 - start
+        v2 = v2 - start - 50000
+        v1 = v1 / (end - 50000 - start) * 255
+        v2 = v2 / (end - 50000 - start) * 255
+        v1 = np.where(v1 < 0, 0, v1)
+        v2 = np.where(v2 < 0, 0, v2)
+    return v1, v2

@@ -250,13 +250,36 @@ def dataset_golden():
     return out
 
 
+def timesurface_golden():
+    """``generate_opticalflow.py:generate_timesurface`` (a numba-jitted function: compiled here as
+    plain Python with an identity ``jit``) on two seeded event sets."""
+    import ast
+    path = os.path.join(rh.REFERENCE_ROOT, "generate_opticalflow.py")
+    with open(path, "r", encoding="utf-8") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    tree.body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "generate_timesurface"]
+    ns = {"np": np, "jit": lambda *a, **k: (lambda f: f)}
+    exec(compile(tree, path, "exec"), ns)  # noqa: S102 - executing the reference is the point
+    out = {}
+    for tag, (H, W, n, t_lo, t_hi, seed) in {"a": (24, 32, 4000, 1000, 301000, 5), "b": (16, 20, 300, 0, 60000, 6)}.items():
+        rng = np.random.default_rng(seed)
+        ev = np.stack([rng.integers(0, W, n), rng.integers(0, H, n), np.sort(rng.integers(t_lo, t_hi, n)),
+                       rng.integers(0, 2, n)], 1).astype(np.float64)
+        v1, v2 = ns["generate_timesurface"](ev, np.zeros((H, W)), np.zeros((H, W)), float(t_hi))
+        out["ts_%s_events" % tag], out["ts_%s_shape" % tag] = ev, np.array([H, W])
+        out["ts_%s_v1" % tag], out["ts_%s_v2" % tag] = np.asarray(v1), np.asarray(v2)
+    np.savez_compressed(os.path.join(GOLDEN, "timesurface.npz"), **out)
+    return out
+
+
 def main():
     assert rh.available(), "reference not mounted at " + rh.REFERENCE_ROOT
     os.makedirs(GOLDEN, exist_ok=True)
     enc = encoder_golden()
     drv = driver_golden()
     dsg = dataset_golden()
-    print("dataset_read.npz:", len(dsg), "arrays")
+    tsg = timesurface_golden()
+    print("dataset_read.npz:", len(dsg), "arrays;", "timesurface.npz:", len(tsg), "arrays")
     print("encoders_small.npz:", len(enc), "arrays;", "drivers_digest.json:",
           sum(len(v) for v in drv.values()), "files")
 
