@@ -389,10 +389,24 @@ taf_tile_ws_kernel(TileParams tp) {
                     constexpr int kPre = 8;
                     constexpr uint32_t kNoRec = 0xFFFFFFFFu;        // d = 2^18-1, pixel 8191: never produced for P <= 2560
                     uint32_t pre[kPre];
+                    // rounds of kAccumThreads records the bin needs (uniform): a small bin (GEN1: ~70
+                    // records) takes a two-round path instead of walking all eight rounds of the unrolled code
+                    const int n_pre = (int)min((uint32_t)kPre, (o1 - o0 + kAccumThreads - 1) / kAccumThreads);
+                    // only compiled into the small-tile instantiations (GEN1-size grids): on large tiles the
+                    // extra branch alone cost 4 % of the kernel
+                    const bool small_bin = SLOTS <= 2 && n_pre <= 2;
+                    if (small_bin) {
 #pragma unroll
-                    for (int i = 0; i < kPre; ++i) {
-                        const uint32_t r = o0 + tid + i * kAccumThreads;
-                        pre[i] = r < o1 ? ring[r & (kWsRing - 1)] : kNoRec;
+                        for (int i = 0; i < 2; ++i) {
+                            const uint32_t r = o0 + tid + i * kAccumThreads;
+                            pre[i] = (i < n_pre && r < o1) ? ring[r & (kWsRing - 1)] : kNoRec;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kPre; ++i) {
+                            const uint32_t r = o0 + tid + i * kAccumThreads;
+                            pre[i] = r < o1 ? ring[r & (kWsRing - 1)] : kNoRec;
+                        }
                     }
                     const bool all_pre = (o1 - o0) <= (uint32_t)(kPre * kAccumThreads);
                     // the consumers must have drained this buffer (its first use needs no wait); the
@@ -406,12 +420,23 @@ taf_tile_ws_kernel(TileParams tp) {
                             for (int r = next_refill; r < drained + kWsStages && r < n_chunks; ++r) issue(r);
                         if (drained + kWsStages > next_refill) next_refill = drained + kWsStages;
                     }
+                    if (small_bin) {
 #pragma unroll
-                    for (int i = 0; i < kPre; ++i) {
-                        if (pre[i] != kNoRec) {
-                            uint2* cell = my_acc + (pre[i] & 0x3FFFu);   // 2 * local pixel + p
-                            atomicAdd(&cell->x, 1u);
-                            atomicAdd(&cell->y, pre[i] >> 14);
+                        for (int i = 0; i < 2; ++i) {
+                            if (pre[i] != kNoRec) {
+                                uint2* cell = my_acc + (pre[i] & 0x3FFFu);   // 2 * local pixel + p
+                                atomicAdd(&cell->x, 1u);
+                                atomicAdd(&cell->y, pre[i] >> 14);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kPre; ++i) {
+                            if (pre[i] != kNoRec) {
+                                uint2* cell = my_acc + (pre[i] & 0x3FFFu);
+                                atomicAdd(&cell->x, 1u);
+                                atomicAdd(&cell->y, pre[i] >> 14);
+                            }
                         }
                     }
                     for (uint32_t r = o0 + tid + kPre * kAccumThreads; r < o1; r += kAccumThreads) {
