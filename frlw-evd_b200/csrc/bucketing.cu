@@ -574,7 +574,9 @@ int make_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n
     const int sms = sm_count() * tiles_per_sm;
     int64_t P = (HW + sms - 1) / sms;
     P = (P + 31) / 32 * 32;
-    if (P > kTafThreads * kMaxSlots) P = kTafThreads * kMaxSlots;
+    // at most 6 pixels per consumer thread (2304), and small enough for the warp-specialised tile kernel's
+    // shared memory at K = 8 (ring + two accumulators + staging tile <= 227 KB  =>  P <= 2240)
+    if (P > kMaxTilePixels) P = kMaxTilePixels;
     if (P < 32) P = 32;
     L.P = (int)P;
     L.n_tiles = (int)((HW + P - 1) / P);

@@ -14,6 +14,7 @@ namespace evrep {
 
 constexpr int kTafThreads = 384;        // threads per tile CTA: 3 warps per SM sub-partition -> up to 168 registers
 constexpr int kMaxSlots = 6;            // pixels per thread held in registers (6 x 384 = 2304 >= 2240)
+constexpr int kMaxTilePixels = 2240;    // largest tile: see make_layout
 constexpr int kChunkRecords = 1024;     // records per TMA bulk copy (4 KB)
 constexpr int kStages = 8;              // ring depth (32 KB in flight per SM)
 constexpr int kBatchBins = 16;          // bins whose offsets are staged in smem at once
