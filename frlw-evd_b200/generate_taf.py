@@ -119,7 +119,7 @@ class HostPipeline:
     leaky/flip/resize/uint8 epilogue) and the device->host copy of chunk c-1.  The FIFO state
     is carried between chunks in a device tensor."""
 
-    def __init__(self, geom: Geometry, plan, K=VOLUME_BINS, abin=ABIN, windows_per_chunk=24, device="cuda"):
+    def __init__(self, geom: Geometry, plan, K=VOLUME_BINS, abin=ABIN, windows_per_chunk=12, device="cuda"):
         self.geom, self.K, self.abin, self.device = geom, K, abin, torch.device(device)
         self.windows = [w if isinstance(w, tuple) else w.as_tuple(abin) for w in plan]
         self.chunks = [(i, min(i + windows_per_chunk, len(self.windows)))
