@@ -67,6 +67,11 @@ SIGNATURES = {
     "evrep_taf_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int64, c_int, c_int]),
     "evrep_taf_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int,
                                  P, c_int64, P, c_int64, P, P, P]),
+    "evrep_taf_stream_ordered_scratch_bytes": (c_int64, [c_int64, c_int, c_int64, c_int, c_int, c_int]),
+    "evrep_taf_stream_ordered": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P,
+                                         c_int, P, c_int64, P, c_int64, P, c_int64, P, P, P]),
+    "evrep_stream_order_violations": (c_int, [P, P, P]),
+    "evrep_events_order_check": (c_int, [P, c_int64, P, P]),
     "evrep_event_volume_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "evrep_event_volume_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int64, c_int, c_int, c_int, P, P, c_int, c_int,
                                           P, c_int64, P, c_int64, P]),

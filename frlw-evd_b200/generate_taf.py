@@ -10,6 +10,7 @@ through the bucketing pass + persistent tile kernel (``ops.taf_stream``).
 from __future__ import annotations
 
 import math
+import os
 import time
 from dataclasses import dataclass
 from typing import List
@@ -131,7 +132,10 @@ class HostPipeline:
         dev = self.device
         self.raw = [torch.empty(max(max_ev, 1) * 8, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.soa = [ops.EventStream.empty(max(max_ev, 1), dev) for _ in range(2)]
-        self.vol = torch.empty((max(max_w, 1), 2 * K, H, W), dtype=torch.float32, device=dev)
+        self.assume_ordered = os.environ.get("EVREP_TAF_PATH", "") != "bucketed"
+        self.fused_u8 = self.assume_ordered and tuple(geom.grid) == tuple(geom.target)
+        self.vol = None if self.fused_u8 else torch.empty((max(max_w, 1), 2 * K, H, W), dtype=torch.float32, device=dev)
+        self.violations = torch.zeros(1, dtype=torch.int32, device=dev)
         self.u8 = [torch.empty((max(max_w, 1), K, 2, Ht, Wt), dtype=torch.uint8, device=dev) for _ in range(2)]
         self.state = ops.taf_fresh_state(geom.grid, K, dev)
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
@@ -157,14 +161,24 @@ class HostPipeline:
             with torch.cuda.stream(self.s_comp):
                 self.s_comp.wait_event(in_done[k])
                 soa = self.soa[k].slice(0, n)
+                # a .dat payload is ordered in time (the reference's loader seeks by bisection on that
+                # assumption); the ordered kernels count violations, `order_violations` reports them
+                soa.ordered = self.assume_ordered
                 ops.decode_dat(self.raw[k][:n * 8], soa)
                 raw_free[k].record(self.s_comp)
                 local = [(w[0] - e0, w[1] - e0, w[2], w[3], w[4]) for w in self.windows[a:b]]
-                vol = self.vol[:b - a]
-                ops.taf_stream(soa, local, self.abin, self.geom.grid, self.K, self.state, self.geom.coord_maps, False, vol)
                 if c >= 2:
                     self.s_comp.wait_event(out_done[k])
-                ops.taf_leaky_u8_batch(vol, self.K, self.geom.target, self.geom.resize_maps, self.u8[k][:b - a])
+                if self.fused_u8:
+                    # no resize between grid and target: the tile kernel writes the file bytes itself
+                    ops.taf_stream(soa, local, self.abin, self.geom.grid, self.K, self.state, self.geom.coord_maps,
+                                   out_u8=self.u8[k][:b - a], want_f32=False)
+                else:
+                    vol = self.vol[:b - a]
+                    ops.taf_stream(soa, local, self.abin, self.geom.grid, self.K, self.state, self.geom.coord_maps, False, vol)
+                    ops.taf_leaky_u8_batch(vol, self.K, self.geom.target, self.geom.resize_maps, self.u8[k][:b - a])
+                if self.assume_ordered:
+                    self.violations += ops.order_violations_tensor(self.device)
                 comp_done[k].record(self.s_comp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(comp_done[k])
@@ -173,6 +187,11 @@ class HostPipeline:
         for s in (self.s_in, self.s_comp, self.s_out):
             start.wait_stream(s)
         return out_host
+
+    def order_violations(self) -> int:
+        """Events found outside the bin their position implies, over all runs so far (synchronises).
+        Non-zero means the payload was not ordered in time: run again with ``EVREP_TAF_PATH=bucketed``."""
+        return int(self.violations.item())
 
 
 def encode_recording_to_files(rec: DeviceRecording, labels, name: str, mode: str, target_dir: str, geom: Geometry,

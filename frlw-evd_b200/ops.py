@@ -7,6 +7,7 @@ raises if the library or a device is missing -- there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -83,15 +84,25 @@ def scratch(kind: str, nbytes: int, device) -> torch.Tensor:
 _workspace = {}
 
 
+def _dev_index(device) -> int:
+    device = torch.device(device)
+    return torch.cuda.current_device() if device.index is None else device.index
+
+
 def workspace(kind: str, nbytes: int, device) -> torch.Tensor:
-    """Grow-only uninitialised scratch (one buffer per device and kind)."""
-    key = (str(device), kind)
+    """Grow-only uninitialised scratch: one buffer per (device, kind, current stream), so that two
+    streams never share one and a buffer is only ever released by the stream that uses it."""
+    key = (_dev_index(device), kind, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspace.get(key)
     if buf is None or buf.numel() < nbytes:
         _workspace[key] = buf = None          # release before growing
         buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
         _workspace[key] = buf
     return buf
+
+
+def _workspace_peek(kind: str, device):
+    return _workspace.get((_dev_index(device), kind, torch.cuda.current_stream(device).cuda_stream))
 
 
 # -------------------------------------------------------------------- event buffers
@@ -102,10 +113,21 @@ class EventStream:
     x: torch.Tensor     # uint16 [n]
     y: torch.Tensor     # uint16 [n]
     p: torch.Tensor     # uint8  [n]
+    ordered: Optional[bool] = None     # timestamps non-decreasing (None = not known yet, see is_ordered)
 
     @property
     def n(self) -> int:
         return int(self.t.shape[0])
+
+    def is_ordered(self) -> bool:
+        """Whether the timestamps are non-decreasing (what ``src/io/psee_loader.py`` assumes of a
+        file).  Checked on the device once per stream (one 4-byte read back) and remembered; the
+        ``*_ordered`` entry points of the library need it."""
+        if self.ordered is None:
+            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            _lib.call("evrep_events_order_check", _ptr(self.t), self.n, _ptr(flag), _stream(self.device))
+            self.ordered = int(flag.item()) == 0
+        return self.ordered
 
     @property
     def device(self):
@@ -123,7 +145,7 @@ class EventStream:
                    torch.empty(n, dtype=torch.uint16, device=device), torch.empty(n, dtype=torch.uint8, device=device))
 
     def slice(self, lo: int, hi: int) -> "EventStream":
-        return EventStream(self.t[lo:hi], self.x[lo:hi], self.y[lo:hi], self.p[lo:hi])
+        return EventStream(self.t[lo:hi], self.x[lo:hi], self.y[lo:hi], self.p[lo:hi], True if self.ordered else None)
 
     def to_aos64(self) -> torch.Tensor:
         """The reference's staging matrix: float64 ``[n,4]`` columns (x, y, t, p)."""
@@ -301,11 +323,17 @@ def taf_bin_aos64(events, shape, K: int, state):
 
 
 def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=None,
-               emit_state_every_window=False, out=None, tile_events=None):
-    """T2: run a list of windows ``(ev_begin, ev_end, start_time, n_bins, fresh)`` through
-    the bucketing pass and the persistent tile kernel.  ``state`` (f32 ``[H,W,2,K]``) is
-    updated IN PLACE.  Returns f32 ``[n_windows, 2K, H, W]``.  ``tile_events``: optional pair
-    of ``torch.cuda.Event(enable_timing=True)`` recorded around the tile kernel."""
+               emit_state_every_window=False, out=None, tile_events=None, out_u8=None, want_f32=True):
+    """T2: run a list of windows ``(ev_begin, ev_end, start_time, n_bins, fresh)`` through the
+    whole-stream TAF kernels.  ``state`` (f32 ``[H,W,2,K]``) is updated IN PLACE.  Returns f32
+    ``[n_windows, 2K, H, W]`` (``None`` with ``want_f32=False``).  ``out_u8``: optional u8
+    ``[n_windows, K, 2, H, W]`` filled with the bytes of the ``bins*`` files (leaky transform +
+    slot flip, ``generate_taf.py:226-235``) straight from the tile kernel.  ``tile_events``:
+    optional pair of ``torch.cuda.Event(enable_timing=True)`` recorded around the tile kernel.
+
+    Time-ordered streams (``ev.is_ordered()``) take the one-pass slice sort
+    (``evrep_taf_stream_ordered``); anything else the general two-pass bucketing
+    (``evrep_taf_stream``).  ``EVREP_TAF_PATH=bucketed`` forces the latter."""
     _need_cuda(ev.t, state)
     H, W = shape
     nw = len(windows)
@@ -314,20 +342,54 @@ def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=N
     for i, w in enumerate(windows):
         arr[i] = _lib.TafWindow(int(w[0]), int(w[1]), int(w[2]), int(w[3]), int(w[4]))
         total_bins += int(w[3])
-    if out is None:
+    if out is None and want_f32:
         out = torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=ev.device)
-    assert state.is_contiguous() and out.is_contiguous()
-    need = _lib.load().evrep_taf_stream_scratch_bytes(ev.n, nw, total_bins, H, W)
+    assert state.is_contiguous() and (out is None or out.is_contiguous())
+    xm, ym = _maps(maps)
+    sensor = maps.sensor_shape if maps is not None else (H, W)
+    lib = _lib.load()
+    ordered = os.environ.get("EVREP_TAF_PATH", "") != "bucketed" and ev.is_ordered()
+    if ordered:
+        need = lib.evrep_taf_stream_ordered_scratch_bytes(ev.n, nw, total_bins, H, W, K)
+        if need < 0:
+            _lib.check(int(need), "evrep_taf_stream_ordered_scratch_bytes")
+        buf = workspace("taf_ordered", need, ev.device)
+        if out_u8 is not None:
+            assert out_u8.is_contiguous() and out_u8.dtype == torch.uint8 and out_u8.numel() >= nw * 2 * K * H * W
+        _lib.call("evrep_taf_stream_ordered", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+                  ctypes.cast(arr, ctypes.c_void_p), nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
+                  int(bool(emit_state_every_window)), _ptr(out), 2 * K * H * W, _ptr(out_u8), 2 * K * H * W,
+                  _ptr(buf), buf.numel(),
+                  _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
+        return out
+    need = lib.evrep_taf_stream_scratch_bytes(ev.n, nw, total_bins, H, W)
     if need < 0:
         _lib.check(int(need), "evrep_taf_stream_scratch_bytes")
     buf = workspace("taf_stream", need, ev.device)
-    xm, ym = _maps(maps)
+    vol = out if out is not None else torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=ev.device)
     _lib.call("evrep_taf_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
-              ctypes.cast(arr, ctypes.c_void_p), nw, int(abin), H, W, K, xm, ym,
-              maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W, _ptr(state),
-              int(bool(emit_state_every_window)), _ptr(out), 2 * K * H * W, _ptr(buf), buf.numel(),
+              ctypes.cast(arr, ctypes.c_void_p), nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
+              int(bool(emit_state_every_window)), _ptr(vol), 2 * K * H * W, _ptr(buf), buf.numel(),
               _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
+    if out_u8 is not None:
+        taf_leaky_u8_batch(vol, K, out=out_u8)
     return out
+
+
+def order_violations_tensor(device) -> torch.Tensor:
+    """Device view (int32 ``[1]``) of the order-violation counter of the last ordered ``taf_stream`` call."""
+    return _workspace_peek("taf_ordered", device)[:4].view(torch.int32)
+
+
+def order_violations(device) -> int:
+    """Events the last ``taf_stream`` call on the ordered path found outside the bin their position
+    implies (0 = the stream really was ordered).  Synchronises the current stream."""
+    buf = _workspace_peek("taf_ordered", device)
+    if buf is None:
+        return 0
+    host = ctypes.c_uint32(0)
+    _lib.call("evrep_stream_order_violations", _ptr(buf), ctypes.byref(host), _stream(buf.device))
+    return int(host.value)
 
 
 def _event(pair, i, device):

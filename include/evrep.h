@@ -195,6 +195,39 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
                      void* scratch, int64_t scratch_bytes,
                      void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream);
 
+/* -------------------------- T2 (time-ordered input): Temporal Active Focus, whole streams ------
+ * Same contract and results as evrep_taf_stream for streams whose timestamps are non-decreasing
+ * over [windows[0].ev_begin, windows[n-1].ev_end) -- what src/io/psee_loader.py hands out, and
+ * what generate_taf.py:188-193 assumes when it seeks by time.  Every bin of a window is then one
+ * contiguous index range, so the two bucketing passes collapse into one: bin ranges by bisection,
+ * one CTA sorts a slice of <= 8188 events by sensor tile in shared memory and writes it back with
+ * one TMA bulk store (9 bytes read + 4 written per event).  The tile kernel keeps the FIFO state
+ * in shared memory as circular buffers with lazy ageing and touches only the cells that received
+ * events (one packed shared-memory atomic per record, one push per active cell per bin).
+ *
+ * out (nullable): f32 [n_windows][2K,H,W].  out_u8 (nullable): u8 [n_windows][K,2,H,W], the bytes of
+ * the bins{K/2} / bins{K} files when no resize follows (leaky transform, slot flip, truncation:
+ * generate_taf.py:226-235), written straight from the tile kernel.  At least one of the two.
+ * Order violations are counted, not repaired: after the call (stream order) the first 4 bytes of
+ * `scratch` hold the number of events whose timestamp lies outside the bin their position implies;
+ * evrep_stream_order_violations copies that word to the host (it synchronises the stream).  With a
+ * non-zero count the result is not the reference's: use evrep_taf_stream for unordered input.
+ * K must be 4 or 8; abin <= 262143; tiles of at most 4096 pixels. */
+int64_t evrep_taf_stream_ordered_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins,
+                                               int H, int W, int K);
+int evrep_taf_stream_ordered(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
+                             int64_t n_events, const evrep_taf_window* windows_host, int n_windows,
+                             int abin, int H, int W, int K,
+                             const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                             float* state_inout, int emit_state_every_window,
+                             float* out, int64_t out_stride, uint8_t* out_u8, int64_t out_u8_stride,
+                             void* scratch, int64_t scratch_bytes,
+                             void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream);
+int evrep_stream_order_violations(const void* scratch, uint32_t* host_out, evrep_stream_t stream);
+/* Counts the adjacent pairs t[i] > t[i+1] into *violations_dev (device memory, 4 bytes); 0 = the
+ * stream may use the *_ordered entry points. */
+int evrep_events_order_check(const uint32_t* t, int64_t n_events, uint32_t* violations_dev, evrep_stream_t stream);
+
 /* ----------------------------------------- V2: Event Volume, whole streams ----------------
  * generate_eventvolume.py:15-42 for a list of ordered, non-overlapping windows in one call:
  * window w holds events [ev_begin, ev_end) and t_norm = (t - t0) / tw (float64, driver :141).
