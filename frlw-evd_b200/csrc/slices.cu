@@ -129,9 +129,14 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     bool store_pending = false;
 
+    // the header of the next slice (its bin, then the bin's descriptor) is fetched while the current slice is sorted,
+    // and its events are pulled into L2 ahead of time
+    uint32_t gbin = 0, gbin_next = 0;
+    BinDesc bd, bd_next;
+    if (blockIdx.x < n_slices) { gbin = sp.slice_bin[blockIdx.x]; bd = sp.bins[gbin]; }
     for (uint32_t s = blockIdx.x; s < n_slices; s += gridDim.x) {
-        const uint32_t gbin = sp.slice_bin[s];
-        const BinDesc bd = sp.bins[gbin];
+        const uint32_t s_next = s + gridDim.x;
+        if (s_next < n_slices) gbin_next = __ldg(sp.slice_bin + s_next);
         const uint32_t part = s - bd.first_slice;
         const uint32_t lo = bd.lo + part * (uint32_t)kSliceMax;
         const uint32_t hi = min(bd.hi, lo + (uint32_t)kSliceMax);
@@ -182,6 +187,18 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
             }
         }
         __syncthreads();                                   // histogram zeroed, padding written
+        if (s_next < n_slices) {
+            bd_next = sp.bins[gbin_next];
+            if (threadIdx.x == 0 && vec_ok) {
+                const uint32_t nlo = (bd_next.lo + (s_next - bd_next.first_slice) * (uint32_t)kSliceMax) & ~15u;
+                const uint32_t nhi = min(bd_next.hi, nlo + (uint32_t)kSliceCap);
+                if (nhi > nlo && (int64_t)nlo + kSliceCap <= n_events) {
+                    const uint32_t n16 = (nhi - nlo + 15u) & ~15u;
+                    l2_prefetch(ev.t + nlo, n16 * 4u); l2_prefetch(ev.x + nlo, n16 * 2u);
+                    l2_prefetch(ev.y + nlo, n16 * 2u); l2_prefetch(ev.p + nlo, n16);
+                }
+            }
+        }
 
         // classify and rank: slot = (tile << 14) | rank inside the tile's run, or kNone
         constexpr uint32_t kNone = 0xFFFFFFFFu;
@@ -259,8 +276,9 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
             __syncthreads();
         }
         const uint32_t total = off[n_tiles];               // padded records of the slice
-        uint16_t* row = sp.off16 + (int64_t)s * sp.pitch;
-        for (int i = threadIdx.x; i <= n_tiles; i += kSortThreads) row[i] = (uint16_t)(off[i] >> 2);
+        // the run table is tile-major: a tile kernel streams its row; neighbouring slices fill the same sectors in L2
+        for (int i = threadIdx.x; i < n_tiles; i += kSortThreads)
+            sp.runs[(int64_t)i * sp.pitch + s] = (off[i] >> 2) | ((off[i + 1] >> 2) << 16);
 #pragma unroll
         for (int k = 0; k < kSortPerThread; ++k)
             if (slot[k] != kNone) sorted[off[slot[k] >> 14] + (slot[k] & 0x3FFFu)] = rec[k];
@@ -275,6 +293,7 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
             if (dyn) atomicOr(&sp.bins[gbin].dyn, dyn);
         }
         store_pending = true;
+        gbin = gbin_next; bd = bd_next;
     }
     if (store_pending && threadIdx.x == 0) bulk_wait_all();
 }
@@ -315,10 +334,10 @@ int choose_tile(int H, int W, int K, TileSmemFn smem_of, int ctas_per_sm, int& P
 int make_slice_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int P, int n_tiles, SliceLayout& L) {
     if (n_events >= (1ll << 31) || TB >= (1ll << 24)) return EVREP_ERR_RANGE;
     L.P = P; L.n_tiles = n_tiles;
-    L.pitch = (n_tiles + 1 + 7) / 8 * 8;
     L.slice_stride = kSliceCap + 4 * n_tiles;
     L.max_slices = n_events / kSliceMax + TB + 1;
-    if (L.max_slices >= (1ll << 31)) return EVREP_ERR_RANGE;
+    if (L.max_slices >= (1ll << 31) - 64) return EVREP_ERR_RANGE;
+    L.pitch = (int)((L.max_slices + 63) / 32 * 32);         // the feed reads 32-slice windows, one ahead
     int64_t o = 0;
     L.o_status = o;   o += 16;
     L.o_wbegin = o;   o += align_up(8ll * n_windows, 16);
@@ -331,7 +350,7 @@ int make_slice_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W,
     o = align_up(o, 256);
     L.o_bins = o;     o += align_up((int64_t)sizeof(BinDesc) * TB, 256);
     L.o_slicebin = o; o += align_up(4ll * L.max_slices, 256);
-    L.o_off16 = o;    o += align_up(2ll * L.max_slices * L.pitch, 256);
+    L.o_runs = o;     o += align_up(4ll * n_tiles * L.pitch, 256);
     L.o_records = o;  o += align_up(4ll * L.max_slices * L.slice_stride, 256);
     L.total = o;
     return EVREP_OK;
@@ -386,7 +405,7 @@ int prepare_slices(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
     sp.w_fresh = reinterpret_cast<const int32_t*>(s + L.o_wfresh);
     sp.bins = reinterpret_cast<BinDesc*>(s + L.o_bins);
     sp.slice_bin = reinterpret_cast<uint32_t*>(s + L.o_slicebin);
-    sp.off16 = reinterpret_cast<uint16_t*>(s + L.o_off16);
+    sp.runs = reinterpret_cast<uint32_t*>(s + L.o_runs);
     sp.records = reinterpret_cast<uint32_t*>(s + L.o_records);
     sp.n_windows = n_windows; sp.TB = (int)TB; sp.n_tiles = n_tiles; sp.P = P; sp.H = H; sp.W = W;
     sp.pitch = L.pitch; sp.slice_stride = L.slice_stride; sp.max_slices = (int)L.max_slices;

@@ -5,8 +5,9 @@
 // of bucketing.cu -- count pass, global scans, scatter pass -- collapses into a purely local
 // job: find the bins' index ranges by bisection, cut every bin into slices of at most 8188
 // events, let one CTA sort a slice by tile in shared memory, write it back with one TMA bulk
-// store and publish the slice's tile offsets in a small table.  A tile kernel then reads its
-// records as one short run per slice (TMA bulk copies into a ring of stages).  Per event:
+// store and publish the slice's tile offsets in a table laid out tile-major (a tile reads its
+// runs as one contiguous row).  A tile kernel then reads its records as one short run per slice
+// (TMA bulk copies into a ring of stages).  Per event:
 // 9 bytes read, 4 written -- no second pass over the events, no global atomics on the data path.
 #pragma once
 
@@ -56,7 +57,7 @@ struct SlicePlan {               // device pointers into the scratch buffer
     const int32_t* w_fresh;
     BinDesc* bins;               // [TB]
     uint32_t* slice_bin;         // [max_slices] global bin of a slice
-    uint16_t* off16;             // [max_slices][pitch]: run of tile i in slice s = records 4 * off[i] .. 4 * off[i + 1] of the slice
+    uint32_t* runs;              // [n_tiles][pitch]: run of tile i in slice s = records 4 * (v & 0xFFFF) .. 4 * (v >> 16) of the slice
     uint32_t* records;           // [max_slices][slice_stride]
     int n_windows, TB, n_tiles, P, H, W, pitch, slice_stride;
     int max_slices;
@@ -69,7 +70,7 @@ struct SliceLayout {
     int P, n_tiles, pitch, slice_stride, ctas_per_sm;
     int64_t max_slices;
     int64_t o_status, o_wbegin, o_wend, o_wstart, o_wnbins, o_wbinbase, o_wfresh, meta_bytes;
-    int64_t o_bins, o_slicebin, o_off16, o_records, total;
+    int64_t o_bins, o_slicebin, o_runs, o_records, total;
 };
 
 // Shared memory a tile CTA needs for a tile of P pixels (K slots), per kernel family.
@@ -94,7 +95,7 @@ int prepare_slices(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
 // one *segment* (the records of one bin, or a piece of it) per stage through a descriptor guarded by
 // mbarriers: FULL[stage] (transaction bytes + the producer's arrival), EMPTY[stage] (one arrival
 // per worker warp once it has read the records).
-constexpr int kFeedStages = 4;
+constexpr int kFeedStages = 6;
 constexpr int kFeedStageRecords = 512;             // 2 KB per stage
 
 enum : uint32_t {
@@ -131,6 +132,16 @@ __device__ __forceinline__ void mbar_add_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS) and its completion hooked to an mbarrier: the arrival fires once all
+// earlier cp.async of the executing thread have landed, and counts as one of the barrier's expected arrivals (.noinc).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+constexpr int kFeedFullCount = 1;                  // FULL[stage]: the publisher's arrival (+ the TMA transaction bytes)
+
 // Producer side of the feed (one warp).  `seq` counts descriptors; stage = seq % kFeedStages.
 struct FeedProducer {
     uint32_t* ring;
@@ -164,47 +175,67 @@ struct FeedProducer {
         acquire();
         publish(0u, flags, age_inc, arg);
     }
+    // ---- the tile's row of the run table, read through a window of 64 consecutive slices (two registers per lane) ----
+    const uint32_t* row;         // runs of this tile, one entry per slice
+    uint32_t win_base;           // slice index of lane 0 of `win_lo`
+    uint32_t win_lo, win_hi;     // entries win_base + lane and win_base + 32 + lane (win_hi is the prefetch)
+    uint32_t n_slices;
+
+    __device__ __forceinline__ void open_row(const SlicePlan& sp, int tile) {
+        row = sp.runs + (int64_t)tile * sp.pitch;
+        n_slices = sp.status[1];
+        win_base = 0;
+        win_lo = lane < n_slices ? __ldg(row + lane) : 0u;
+        win_hi = 32u + lane < n_slices ? __ldg(row + 32 + lane) : 0u;
+    }
+    // Entry of slice s0 + lane (0 beyond the window's reach or `count`): slices s0 .. s0 + 31 must start inside the window.
+    __device__ __forceinline__ uint32_t entries(uint32_t s0, uint32_t count) {
+        while (s0 >= win_base + 32u) {                   // slide: the prefetched half becomes current, the next one is requested
+            win_base += 32u;
+            win_lo = win_hi;
+            win_hi = win_base + 32u + lane < n_slices ? __ldg(row + win_base + 32 + lane) : 0u;
+        }
+        const uint32_t k = s0 - win_base + lane;         // 0 .. 62
+        const uint32_t from_lo = __shfl_sync(0xFFFFFFFFu, win_lo, k & 31u);
+        const uint32_t from_hi = __shfl_sync(0xFFFFFFFFu, win_hi, k & 31u);
+        return lane < count ? (k < 32u ? from_lo : from_hi) : 0u;
+    }
     // All records of this tile in bin `gbin` -> one or more segments; returns false when the tile has none.
-    __device__ bool feed_bin(const SlicePlan& sp, int tile, uint32_t gbin, const BinDesc& bd, uint32_t age_inc);
+    __device__ bool feed_bin(const SlicePlan& sp, uint32_t gbin, uint32_t first_slice, uint32_t parts, uint32_t dyn, uint32_t age_inc);
 };
 
-__device__ __forceinline__ bool FeedProducer::feed_bin(const SlicePlan& sp, int tile, uint32_t gbin, const BinDesc& bd,
-                                                       uint32_t age_inc) {
-    const uint32_t parts = slice_parts(bd.lo, bd.hi);
-    const uint32_t wide = (bd.dyn & kBinBigD) ? kSegWide : 0u;
+__device__ __forceinline__ bool FeedProducer::feed_bin(const SlicePlan& sp, uint32_t gbin, uint32_t first_slice, uint32_t parts,
+                                                       uint32_t dyn, uint32_t age_inc) {
+    const uint32_t wide = (dyn & kBinBigD) ? kSegWide : 0u;
     // pass 1 (bins of more than 32 slices only): the bin's total, so that the last segment is known when it is built
     uint32_t total = 0;
-    uint32_t a = 0, b = 0;
-    auto load_runs = [&](uint32_t c0) {
-        a = 0; b = 0;
-        if (c0 + lane < parts) {
-            const uint16_t* row = sp.off16 + (int64_t)(bd.first_slice + c0 + lane) * sp.pitch + tile;
-            a = __ldg(row); b = __ldg(row + 1);
-        }
-    };
     if (parts > 32u) {
         for (uint32_t c0 = 0; c0 < parts; c0 += 32u) {
-            load_runs(c0);
-            total += __reduce_add_sync(0xFFFFFFFFu, (b - a) * 4u);
+            const uint32_t v = __ldg(row + first_slice + c0 + (c0 + lane < parts ? lane : 0u));
+            total += __reduce_add_sync(0xFFFFFFFFu, c0 + lane < parts ? ((v >> 16) - (v & 0xFFFFu)) * 4u : 0u);
         }
     }
     uint32_t q0 = 0;                                    // records of the bin placed so far
     bool open = false;                                  // the stage holding record q0 is acquired and not yet published
     for (uint32_t c0 = 0; c0 < parts; c0 += 32u) {
-        load_runs(c0);
+        const uint32_t cnt = parts - c0 < 32u ? parts - c0 : 32u;
+        uint32_t v;
+        if (parts <= 32u) v = entries(first_slice, cnt);
+        else v = c0 + lane < parts ? __ldg(row + first_slice + c0 + lane) : 0u;
+        const uint32_t a = v & 0xFFFFu, b = v >> 16;
         const uint32_t len = (b - a) * 4u;
         uint32_t incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += v;
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
         }
         const uint32_t chunk_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         if (parts <= 32u) total = chunk_total;
         if (total == 0u) return false;
         if (chunk_total == 0u) continue;
         const uint32_t start = q0 + incl - len, end = q0 + incl;          // this lane's run, bin-relative
-        const uint32_t* src = sp.records + (int64_t)(bd.first_slice + c0 + lane) * sp.slice_stride + a * 4u;
+        const uint32_t* src = sp.records + (int64_t)(first_slice + c0 + lane) * sp.slice_stride + a * 4u;
         const uint32_t q1 = q0 + chunk_total;
         for (uint32_t sb = q0 / kFeedStageRecords * kFeedStageRecords; sb < q1; sb += kFeedStageRecords) {
             if (!open) { acquire(); open = true; }

@@ -25,11 +25,15 @@ namespace evrep {
 
 constexpr int kTsWorkers = 256;                    // worker threads (8 warps)
 constexpr int kTsThreads = kTsWorkers + 32;        // + the producer warp
-constexpr int kTsWorkerWarps = kTsWorkers / 32;
+constexpr int kTsWarps = kTsWorkers / 32;
 constexpr int kBarWorkers = 1;                     // named barrier of the worker warps
 constexpr uint32_t kCountShift = 23;               // packed accumulator: count in bits 23..31, sum of d below
+constexpr uint32_t kSumMask = (1u << kCountShift) - 1u;
 constexpr uint32_t kHotCount = 256;                // a cell that reaches this count in one bin forces the exact path
 constexpr int kRebaseAlways = 8;                   // A never exceeds this: rebase inside a window when it gets there
+constexpr int kHeldSegments = 2;                   // segments of a bin whose records a thread keeps in registers for the push
+constexpr int kPerSeg = kFeedStageRecords / kTsWorkers;   // records per thread per segment
+static_assert(kFeedStageRecords % kTsWorkers == 0, "a stage is a whole number of records per worker thread");
 
 struct TafSliceParams {
     SlicePlan sp;
@@ -39,18 +43,18 @@ struct TafSliceParams {
     uint8_t* out_u8;       // optional: u8 [n_windows][K,2,H,W], leaky transform + slot flip (generate_taf.py:226-235)
     int64_t out_u8_stride;
     int emit_state;        // write the state after every window (always after the last)
+    int vec_out;           // out / out_u8 rows allow 16-byte / 4-byte vector stores (4 pixels per thread)
     float span;            // f32(abin + 1e-8)
 };
 
 struct TafSliceSmem {
-    int state, acc, list, head, ctrl, feed_base, total;
+    int state, acc, head, ctrl, feed_base, total;
     __host__ __device__ TafSliceSmem(int P, int K) {
         int o = 0;
         state = o; o += K * 2 * P * 4;                  // u[K][2P]
         acc = o;   o += 2 * 2 * P * 4;                  // two buffers of packed {count | sum d} per cell
-        list = o;  o += 2 * 2 * P * 2;                  // two active lists (u16 cells)
         head = o;  o += 2 * P; o = (o + 15) / 16 * 16;  // next slot to overwrite, per cell
-        ctrl = o;  o += 32;                             // list counters [2], hot flags [2]
+        ctrl = o;  o += 16;                             // hot counters [2] (monotonic)
         feed_base = o;
         total = FeedSmem(o).total;
     }
@@ -58,30 +62,21 @@ struct TafSliceSmem {
 
 static size_t taf_slice_smem(int P, int K) { return (size_t)TafSliceSmem(P, K).total; }
 
-__device__ __forceinline__ void worker_sync() { named_sync(kBarWorkers, kTsWorkers); }
-
-// generate_taf.py:69-76 on one value: 255 * max(0, 1 - log1p(-v) / 8.7), truncated to uint8
-__device__ __forceinline__ uint32_t leaky_u8(float v) {
-    const float r = 1.0f - __fdiv_rn(log1pf(-v), 8.7f);          // same arithmetic as taf_leaky_u8_kernel
-    return (uint32_t)(int)((r < 0.0f ? 0.0f : r) * 255.0f);
+// generate_taf.py:69-76 on one value, 255 * max(0, 1 - log1p(-v) / 8.7) truncated to uint8, with the logarithm
+// from MUFU.LG2 (v <= 0, so 1 - v >= 1): within 1e-5 of the float32 reference before truncation
+__device__ __forceinline__ uint32_t leaky_u8_fast(float v) {
+    const float r = fmaf(__log2f(1.0f - v), -0.6931471805599453f / 8.7f, 1.0f);
+    return (uint32_t)(int)(fmaxf(r, 0.0f) * 255.0f);
 }
 
 template <int K>
-__global__ void __launch_bounds__(kTsThreads)
+__global__ void __launch_bounds__(kTsThreads, 2)
 taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
     const SlicePlan& sp = tp.sp;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = sp.P;
     const TafSliceSmem lay(P, K);
     const FeedSmem fs(lay.feed_base);
-    float* u = reinterpret_cast<float*>(smem_raw + lay.state);            // [K][2P]
-    uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw + lay.acc);      // [2][2P]
-    uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + lay.list);    // [2][2P]
-    uint8_t* head = smem_raw + lay.head;                                  // [2P]
-    uint32_t* list_count = reinterpret_cast<uint32_t*>(smem_raw + lay.ctrl);   // [2], monotonic
-    uint32_t* hot = list_count + 2;                                       // [2]
-    const uint32_t* ring = reinterpret_cast<const uint32_t*>(smem_raw + fs.ring);
-    const SegDesc* desc = reinterpret_cast<const SegDesc*>(smem_raw + fs.desc);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + fs.full);
     uint64_t* empty = reinterpret_cast<uint64_t*>(smem_raw + fs.empty);
 
@@ -92,9 +87,7 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
     const int C = 2 * P;                                 // cells of the tile: cell = p * P + pixel
 
     if (tid == 0) {
-        for (int s = 0; s < kFeedStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kTsWorkerWarps); }
-        list_count[0] = list_count[1] = 0u;
-        hot[0] = hot[1] = 0u;
+        for (int s = 0; s < kFeedStages; ++s) { mbar_init(full + s, kFeedFullCount); mbar_init(empty + s, kTsWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -103,25 +96,24 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
         // ================================== producer warp ==================================
         FeedProducer fp;
         fp.init(smem_raw, fs);
+        fp.open_row(sp, tile);
         for (int w = 0; w < sp.n_windows; ++w) {
             if (w > 0 && sp.w_fresh[w]) fp.control(kSegReset, 0u, (uint32_t)w);
             const int g0 = sp.w_binbase[w], g1 = sp.w_binbase[w + 1];
             uint32_t pend_age = 0;                       // bins that age the tile without bringing it records
             for (int gb = g0; gb < g1; gb += 32) {
                 // descriptors of 32 bins at a time, one per lane
-                BinDesc mine;
-                mine.lo = mine.hi = 0; mine.t0 = 0; mine.first_slice = 0; mine.flags = 0; mine.dyn = 0; mine.win = 0;
-                if (gb + lane < g1) mine = sp.bins[gb + lane];
+                uint32_t first = 0, parts = 0, dyn = 0;
+                if (gb + lane < g1) {
+                    const BinDesc* bd = sp.bins + gb + lane;
+                    first = bd->first_slice; parts = slice_parts(bd->lo, bd->hi); dyn = bd->dyn;
+                }
                 const int nb = min(32, g1 - gb);
                 for (int k = 0; k < nb; ++k) {
-                    BinDesc bd;
-                    bd.lo = __shfl_sync(0xFFFFFFFFu, mine.lo, k);
-                    bd.hi = __shfl_sync(0xFFFFFFFFu, mine.hi, k);
-                    bd.first_slice = __shfl_sync(0xFFFFFFFFu, mine.first_slice, k);
-                    bd.dyn = __shfl_sync(0xFFFFFFFFu, mine.dyn, k);
-                    bd.t0 = 0; bd.flags = 0; bd.win = 0;
-                    if (!(bd.dyn & kBinAny)) continue;   // nobody saw an event: no ageing (generate_taf.py:40-41)
-                    if (fp.feed_bin(sp, tile, (uint32_t)(gb + k), bd, pend_age + 1u)) pend_age = 0;
+                    const uint32_t k_dyn = __shfl_sync(0xFFFFFFFFu, dyn, k);
+                    if (!(k_dyn & kBinAny)) continue;    // nobody saw an event: no ageing (generate_taf.py:40-41)
+                    const uint32_t k_first = __shfl_sync(0xFFFFFFFFu, first, k), k_parts = __shfl_sync(0xFFFFFFFFu, parts, k);
+                    if (fp.feed_bin(sp, (uint32_t)(gb + k), k_first, k_parts, k_dyn, pend_age + 1u)) pend_age = 0;
                     else ++pend_age;
                 }
             }
@@ -131,111 +123,155 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
     }
 
     // ==================================== worker warps ====================================
-    const int wid = tid >> 5;
+    auto worker_sync = [] { named_sync(kBarWorkers, kTsWorkers); };
+    // everything below addresses shared memory by 32-bit shared addresses (LDS / STS / ATOMS)
+    const uint32_t a_u = smem_u32(smem_raw + lay.state);          // f32 [K][2P]
+    const uint32_t a_acc = smem_u32(smem_raw + lay.acc);          // u32 [2][2P]
+    const uint32_t a_head = smem_u32(smem_raw + lay.head);        // u8 [2P]
+    const uint32_t a_hot = smem_u32(smem_raw + lay.ctrl);         // u32 [2]
+    const uint32_t a_ring = smem_u32(smem_raw + fs.ring);
+    const uint32_t a_desc = smem_u32(smem_raw + fs.desc);
+    const uint32_t row_bytes = (uint32_t)C * 4u;                  // one slot row of the state
+
     const bool first_fresh = sp.w_fresh[0] != 0;
+    if (tid < 2) sst_u32(a_hot + tid * 4u, 0u);
     // state in: u = v (A = 0), heads at 0 -- slot e of a cell holds FIFO position e (K - 1 = newest)
     for (int c = tid; c < C; c += kTsWorkers) {
         const int p = c >= P ? 1 : 0, pix = c - p * P;
-        head[c] = 0;
-        acc[c] = 0u; acc[C + c] = 0u;
+        sst_u8(a_head + c, 0u);
+        sst_u32(a_acc + c * 4u, 0u); sst_u32(a_acc + (C + c) * 4u, 0u);
         if (pix < npix && !first_fresh) {
             const float4* src = reinterpret_cast<const float4*>(tp.state + ((pix0 + pix) * 2 + p) * K);
 #pragma unroll
             for (int q = 0; q < K / 4; ++q) {
                 const float4 f = __ldg(src + q);
-                u[(4 * q + 0) * C + c] = f.x; u[(4 * q + 1) * C + c] = f.y;
-                u[(4 * q + 2) * C + c] = f.z; u[(4 * q + 3) * C + c] = f.w;
+                sst_f32(a_u + (4 * q + 0) * row_bytes + c * 4u, f.x); sst_f32(a_u + (4 * q + 1) * row_bytes + c * 4u, f.y);
+                sst_f32(a_u + (4 * q + 2) * row_bytes + c * 4u, f.z); sst_f32(a_u + (4 * q + 3) * row_bytes + c * 4u, f.w);
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < K; ++e) u[e * C + c] = kTafInit;
+            for (int e = 0; e < K; ++e) sst_f32(a_u + e * row_bytes + c * 4u, kTafInit);
         }
     }
     worker_sync();
 
     int A = 0;                                           // ageing steps not yet materialised in `u`
-    int buf = 0;
-    uint32_t list_base[2] = {0u, 0u};
+    uint32_t acc_cur = a_acc, acc_alt = a_acc + row_bytes;    // accumulator of the open bin / of the previous one
+    uint32_t hot_cur = a_hot, hot_alt = a_hot + 4u;
+    uint32_t hot_seen_cur = 0u, hot_seen_alt = 0u;       // last values seen of the two monotonic hot counters
+    uint32_t held[kHeldSegments * kPerSeg];              // this thread's records of the open bin (the push visits them again)
+#pragma unroll
+    for (int i = 0; i < kHeldSegments * kPerSeg; ++i) held[i] = kNullRecord;
+    int seg_in_bin = 0;                                  // segments of the open bin seen so far
     bool dirty = false;                                  // pushes since the last worker barrier
-    bool wide_open = false;                              // inside a bin that uses the two-word accumulators
 
-    // add one record to the packed accumulator of `b`; returns through `first` whether the cell was untouched
-    auto append = [&](int b, bool first, uint32_t cell) {
-        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, first);
-        if (mask) {
-            uint32_t base = 0;
-            const int leader = __ffs(mask) - 1;
-            if (lane == leader) base = atomicAdd(&list_count[b], (uint32_t)__popc(mask));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (first) list[b * C + (base - list_base[b]) + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)cell;
-        }
+    // one value into the circular buffer of a cell: mean(t_norm) - 1 = S / (n span) - 1 (generate_taf.py:23-27), stored as u = v + A
+    auto push_cell = [&](uint32_t cell, uint32_t n, uint32_t s, float fa) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)n * tp.span));
+        const uint32_t h = sld_u8(a_head + cell);
+        sst_f32(a_u + h * row_bytes + cell * 4u, fmaf((float)s, r, fa));
+        sst_u8(a_head + cell, (h + 1u) & (uint32_t)(K - 1));
     };
-    auto accumulate_packed = [&](int b, uint32_t rec) {
-        bool first = false;
-        const uint32_t cell = rec & 0x3FFFu;
-        if (rec != kNullRecord) {
-            const uint32_t old = atomicAdd(&acc[b * C + cell], (1u << kCountShift) + (rec >> 14));
-            first = old == 0u;
-            if ((old >> kCountShift) >= kHotCount) hot[b] = 1u;
-        }
-        append(b, first, cell);
-    };
-    // two-word accumulators: counts in buffer b, sums of d in the other one
-    auto accumulate_wide = [&](int b, uint32_t rec) {
-        bool first = false;
-        const uint32_t cell = rec & 0x3FFFu;
-        if (rec != kNullRecord) {
-            first = atomicAdd(&acc[b * C + cell], 1u) == 0u;
-            atomicAdd(&acc[(b ^ 1) * C + cell], rec >> 14);
-        }
-        append(b, first, cell);
-    };
-    // push the mean of every active cell: one store into its circular buffer
-    auto push = [&](int b, bool wide) {
-        const uint32_t count = list_count[b] - list_base[b];
-        const float fa = (float)(A - 1);
-        for (uint32_t j = tid; j < count; j += kTsWorkers) {
-            const uint32_t cell = list[b * C + j];
-            uint32_t n, s;
-            if (wide) {
-                n = acc[b * C + cell]; s = acc[(b ^ 1) * C + cell];
-                acc[b * C + cell] = 0u; acc[(b ^ 1) * C + cell] = 0u;
-            } else {
-                const uint32_t xw = acc[b * C + cell];
-                acc[b * C + cell] = 0u;
-                n = xw >> kCountShift; s = xw & ((1u << kCountShift) - 1u);
+    // every record of this tile in bin `gbin`, straight from global memory (the exact path)
+    auto for_bin_records = [&](uint32_t gbin, auto&& fn) {
+        const BinDesc bd = sp.bins[gbin];
+        const uint32_t parts = slice_parts(bd.lo, bd.hi);
+        for (uint32_t c = tid >> 5; c < parts; c += kTsWarps) {
+            const int64_t s = (int64_t)bd.first_slice + c;
+            const uint32_t v = sp.runs[(int64_t)tile * sp.pitch + s];
+            const uint32_t* src = sp.records + s * sp.slice_stride + (v & 0xFFFFu) * 4u;
+            const uint32_t n = ((v >> 16) - (v & 0xFFFFu)) * 4u;
+            for (uint32_t i = lane; i < n; i += 32u) {
+                const uint32_t rec = __ldg(src + i);
+                if (rec != kNullRecord) fn(rec);
             }
-            // mean(t_norm) - 1 = S / (n span) - 1 (generate_taf.py:23-27), stored as u = v + A
-            float r;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)n * tp.span));
-            const uint32_t h = head[cell];
-            u[h * C + cell] = fmaf((float)s, r, fa);
-            head[cell] = (uint8_t)((h + 1u) & (uint32_t)(K - 1));
         }
-        list_base[b] += count;
     };
-    // v = u - A for every cell (FIFO order restored); optionally written back (rebase)
-    auto sweep = [&](float* o, uint8_t* o8, bool write_state, bool rebase) {
+
+    // v = u - A for every cell, FIFO order restored, written to the window tensor / the uint8 file bytes / the state;
+    // u is rebased (u = v) in passing.  Four consecutive pixels per thread when the rows allow vector stores.
+    auto sweep = [&](float* o, uint8_t* o8, bool write_state) {
         const float fa = (float)A;
+        if (tp.vec_out) {
+            const int quads = (npix + 3) >> 2;           // npix is a multiple of 4 here
+            for (int q = tid; q < 2 * quads; q += kTsWorkers) {
+                const int p = q >= quads ? 1 : 0, pix = (q - p * quads) * 4, c = p * P + pix;
+                const uint32_t h4 = sld_u32(a_head + c);
+                float4 r[K];
+                const uint32_t addr = a_u + (uint32_t)c * 4u;
+#pragma unroll
+                for (int e = 0; e < K; ++e) r[e] = sld_v4f(addr + e * row_bytes);     // all loads in flight before the first use
+#pragma unroll
+                for (int e = 0; e < K; ++e) {
+                    r[e].x -= fa; r[e].y -= fa; r[e].z -= fa; r[e].w -= fa;
+                    sst_v4f(addr + e * row_bytes, r[e]);
+                }
+                // rotate each pixel's slots into FIFO order: position e = slot (head + e) mod K
+                float v[4][K];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t h = (h4 >> (8 * j)) & 0xFFu;
+                    float a[K];
+#pragma unroll
+                    for (int e = 0; e < K; ++e) a[e] = j == 0 ? r[e].x : j == 1 ? r[e].y : j == 2 ? r[e].z : r[e].w;
+#pragma unroll
+                    for (int sh = 1; sh < K; sh <<= 1) {
+                        const bool on = (h & (uint32_t)sh) != 0u;
+                        float t[K];
+#pragma unroll
+                        for (int e = 0; e < K; ++e) t[e] = on ? a[(e + sh) & (K - 1)] : a[e];
+#pragma unroll
+                        for (int e = 0; e < K; ++e) a[e] = t[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < K; ++e) v[j][e] = a[e];
+                }
+                if (o) {
+                    float* row = o + (int64_t)p * HW + pix;
+#pragma unroll
+                    for (int e = 0; e < K; ++e, row += 2 * HW)
+                        __stcs(reinterpret_cast<float4*>(row), make_float4(v[0][e], v[1][e], v[2][e], v[3][e]));
+                }
+                if (o8) {
+                    // [K,2,H,W] with slot 0 = newest bin (np.flip of the [K,2,H,W] view)
+                    uint8_t* row = o8 + ((int64_t)(K - 1) * 2 + p) * HW + pix;
+#pragma unroll
+                    for (int e = 0; e < K; ++e, row -= 2 * HW) {
+                        const uint32_t b4 = leaky_u8_fast(v[0][e]) | (leaky_u8_fast(v[1][e]) << 8) | (leaky_u8_fast(v[2][e]) << 16) |
+                                            (leaky_u8_fast(v[3][e]) << 24);
+                        *reinterpret_cast<uint32_t*>(row) = b4;
+                    }
+                }
+                if (write_state) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4* dst = reinterpret_cast<float4*>(tp.state + ((pix0 + pix + j) * 2 + p) * K);
+#pragma unroll
+                        for (int qq = 0; qq < K / 4; ++qq) dst[qq] = make_float4(v[j][4 * qq], v[j][4 * qq + 1], v[j][4 * qq + 2], v[j][4 * qq + 3]);
+                    }
+                }
+            }
+            return;
+        }
         for (int c = tid; c < C; c += kTsWorkers) {
             const int p = c >= P ? 1 : 0, pix = c - p * P;
             if (pix >= npix) continue;
-            const uint32_t h = head[c];
+            const uint32_t h = sld_u8(a_head + c);
             float v[K];
 #pragma unroll
-            for (int e = 0; e < K; ++e) v[e] = u[((h + e) & (K - 1)) * C + c] - fa;
-            if (rebase) {
-#pragma unroll
-                for (int e = 0; e < K; ++e) u[((h + e) & (K - 1)) * C + c] = v[e];
+            for (int e = 0; e < K; ++e) {
+                const uint32_t addr = a_u + ((h + e) & (K - 1)) * row_bytes + (uint32_t)c * 4u;
+                v[e] = __uint_as_float(sld_u32(addr)) - fa;
+                sst_f32(addr, v[e]);
             }
             if (o) {
 #pragma unroll
                 for (int e = 0; e < K; ++e) __stcs(o + (int64_t)(2 * e + p) * HW + pix, v[e]);
             }
             if (o8) {
-                // [K,2,H,W] with slot 0 = newest bin (np.flip of the [K,2,H,W] view)
 #pragma unroll
-                for (int e = 0; e < K; ++e) o8[((int64_t)(K - 1 - e) * 2 + p) * HW + pix] = (uint8_t)leaky_u8(v[e]);
+                for (int e = 0; e < K; ++e) o8[((int64_t)(K - 1 - e) * 2 + p) * HW + pix] = (uint8_t)leaky_u8_fast(v[e]);
             }
             if (write_state) {
                 float4* dst = reinterpret_cast<float4*>(tp.state + ((pix0 + pix) * 2 + p) * K);
@@ -246,79 +282,118 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
     };
 
     for (uint32_t seq = 0;; ++seq) {
-        const int slot = (int)(seq % kFeedStages);
+        const uint32_t slot = seq % kFeedStages;
         mbar_wait(full + slot, (seq / kFeedStages) & 1u);
-        const SegDesc d = desc[slot];
-        if (d.flags & kSegReset) {
+        const uint4 dd = sld_v4(a_desc + slot * 16u);
+        const uint32_t n_rec = dd.x, flags = dd.y, age_inc = dd.z, arg = dd.w;
+        if (flags & kSegReset) {
             if (dirty) { worker_sync(); dirty = false; }
             for (int c = tid; c < C; c += kTsWorkers) {
-                head[c] = 0;
+                sst_u8(a_head + c, 0u);
 #pragma unroll
-                for (int e = 0; e < K; ++e) u[e * C + c] = kTafInit;
+                for (int e = 0; e < K; ++e) sst_f32(a_u + e * row_bytes + c * 4u, kTafInit);
             }
             A = 0;
         }
-        const bool wide = (d.flags & kSegWide) != 0;
-        if (d.n_rec) {
-            if (wide && !wide_open) {
-                // the other accumulator buffer must be idle: everybody has finished the previous push
-                worker_sync(); dirty = false; wide_open = true;
+        const bool wide = (flags & kSegWide) != 0;         // offsets beyond the packed word: the bin takes the exact path
+        if (n_rec && !wide) {
+            // one packed atomic per record; the records stay in registers so that the push can visit their cells again
+            const uint32_t recs = a_ring + slot * (kFeedStageRecords * 4u) + (uint32_t)tid * 4u;
+            uint32_t mine[kPerSeg];
+#pragma unroll
+            for (int j = 0; j < kPerSeg; ++j)
+                mine[j] = (uint32_t)(tid + j * kTsWorkers) < n_rec ? sld_u32(recs + j * (kTsWorkers * 4u)) : kNullRecord;
+#pragma unroll
+            for (int j = 0; j < kPerSeg; ++j) {
+                if (mine[j] != kNullRecord) {
+                    const uint32_t old = satom_add(acc_cur + (mine[j] & 0x3FFFu) * 4u, (1u << kCountShift) + (mine[j] >> 14));
+                    if ((old >> kCountShift) >= kHotCount) sred_add(hot_cur, 1u);
+                }
             }
-            const uint32_t* recs = ring + slot * kFeedStageRecords;
-            for (uint32_t i0 = (uint32_t)wid * 32u; i0 < d.n_rec; i0 += kTsWorkers) {
-                const uint32_t i = i0 + lane;
-                const uint32_t rec = i < d.n_rec ? recs[i] : kNullRecord;
-                if (wide) accumulate_wide(buf, rec); else accumulate_packed(buf, rec);
-            }
+#pragma unroll
+            for (int g = 0; g < kHeldSegments; ++g)
+                if (seg_in_bin == g) {
+#pragma unroll
+                    for (int j = 0; j < kPerSeg; ++j) held[g * kPerSeg + j] = mine[j];
+                }
+            ++seg_in_bin;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);           // this warp is done with the stage
-        A += (int)d.age_inc;
-        if (d.flags & kSegBinEnd) {
+        A += (int)age_inc;
+        if (flags & kSegBinEnd) {
             worker_sync();                                   // the bin is accumulated; earlier pushes are complete
-            bool exact = wide;
-            if (!wide && hot[buf]) {
-                // some cell overflowed the packed word: clear what the bin touched and accumulate it again from
-                // global memory with two-word accumulators
-                const uint32_t count = list_count[buf] - list_base[buf];
-                for (uint32_t j = tid; j < count; j += kTsWorkers) acc[buf * C + list[buf * C + j]] = 0u;
-                list_base[buf] += count;
+            const float fa = (float)(A - 1);
+            const uint32_t hot_now = sld_u32(hot_cur);
+            const bool exact = wide || hot_now != hot_seen_cur;
+            hot_seen_cur = hot_now;
+            if (!exact) {
+                if (seg_in_bin <= kHeldSegments) {
+                    // whoever exchanges a cell's word first gets its content and pushes; later visitors read zero
+#pragma unroll
+                    for (int i = 0; i < kHeldSegments * kPerSeg; ++i) {
+                        if (held[i] != kNullRecord) {
+                            const uint32_t cell = held[i] & 0x3FFFu;
+                            const uint32_t xw = satom_exch(acc_cur + cell * 4u, 0u);
+                            if (xw) push_cell(cell, xw >> kCountShift, xw & kSumMask, fa);
+                        }
+                    }
+                } else {
+                    // a bin of more than two segments: scan the tile's accumulators instead
+                    for (int c = tid; c < C; c += kTsWorkers) {
+                        const uint32_t xw = sld_u32(acc_cur + c * 4u);
+                        if (xw) { sst_u32(acc_cur + c * 4u, 0u); push_cell((uint32_t)c, xw >> kCountShift, xw & kSumMask, fa); }
+                    }
+                }
+                dirty = true;
+                { const uint32_t t = acc_cur; acc_cur = acc_alt; acc_alt = t; }
+                { const uint32_t t = hot_cur; hot_cur = hot_alt; hot_alt = t; }
+                { const uint32_t t = hot_seen_cur; hot_seen_cur = hot_seen_alt; hot_seen_alt = t; }
+            } else {
+                // Exact path (a cell gathered >= 256 events, or offsets beyond 32767): the bin is read again from global
+                // memory, twice -- counts, parked in the slot the mean will go to, then sums of (d + 1) -- so one
+                // accumulator word per cell suffices.  Rare; five extra barriers.
+                for (int c = tid; c < C; c += kTsWorkers) sst_u32(acc_cur + c * 4u, 0u);
                 worker_sync();
-                if (tid == 0) hot[buf] = 0u;
-                const BinDesc bd = sp.bins[d.arg];
-                const uint32_t parts = slice_parts(bd.lo, bd.hi);
-                for (uint32_t c = wid; c < parts; c += kTsWorkerWarps) {
-                    const int64_t s = (int64_t)bd.first_slice + c;
-                    const uint32_t a = sp.off16[s * sp.pitch + tile], b = sp.off16[s * sp.pitch + tile + 1];
-                    const uint32_t* src = sp.records + s * sp.slice_stride + a * 4u;
-                    const uint32_t n = (b - a) * 4u;
-                    for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
-                        const uint32_t i = i0 + lane;
-                        accumulate_wide(buf, i < n ? __ldg(src + i) : kNullRecord);
+                for_bin_records(arg, [&](uint32_t rec) { sred_add(acc_cur + (rec & 0x3FFFu) * 4u, 1u); });
+                worker_sync();
+                for (int c = tid; c < C; c += kTsWorkers) {
+                    const uint32_t n = sld_u32(acc_cur + c * 4u);
+                    if (n) { sst_u32(a_u + sld_u8(a_head + c) * row_bytes + c * 4u, n); sst_u32(acc_cur + c * 4u, 0u); }
+                }
+                worker_sync();
+                for_bin_records(arg, [&](uint32_t rec) { sred_add(acc_cur + (rec & 0x3FFFu) * 4u, (rec >> 14) + 1u); });
+                worker_sync();
+                for (int c = tid; c < C; c += kTsWorkers) {
+                    const uint32_t s1 = sld_u32(acc_cur + c * 4u);
+                    if (s1) {
+                        const uint32_t n = sld_u32(a_u + sld_u8(a_head + c) * row_bytes + c * 4u);
+                        sst_u32(acc_cur + c * 4u, 0u);
+                        push_cell((uint32_t)c, n, s1 - n, fa);
                     }
                 }
                 worker_sync();
-                exact = true;
+                dirty = false;
             }
-            push(buf, exact);
-            if (exact) { worker_sync(); dirty = false; wide_open = false; }    // both buffers are clean again
-            else { dirty = true; buf ^= 1; }
+#pragma unroll
+            for (int i = 0; i < kHeldSegments * kPerSeg; ++i) held[i] = kNullRecord;
+            seg_in_bin = 0;
         }
-        if (d.flags & kSegEmit) {
+        if (flags & kSegEmit) {
             if (dirty) { worker_sync(); dirty = false; }
-            const bool last = (d.flags & kSegDone) != 0;
+            const bool last = (flags & kSegDone) != 0;
             // every emission rebases (u = v, A = 0): the state after a window does not depend on how the
             // windows are split over launches, so split launches == one launch, bit for bit
-            float* o = tp.out ? tp.out + (int64_t)d.arg * tp.out_stride + pix0 : nullptr;
-            uint8_t* o8 = tp.out_u8 ? tp.out_u8 + (int64_t)d.arg * tp.out_u8_stride + pix0 : nullptr;
-            sweep(o, o8, tp.emit_state || last, true);
+            float* o = tp.out ? tp.out + (int64_t)arg * tp.out_stride + pix0 : nullptr;
+            uint8_t* o8 = tp.out_u8 ? tp.out_u8 + (int64_t)arg * tp.out_u8_stride + pix0 : nullptr;
+            sweep(o, o8, tp.emit_state || last);
             A = 0;
         } else if (A >= kRebaseAlways) {
             if (dirty) { worker_sync(); dirty = false; }
-            sweep(nullptr, nullptr, false, true);
+            sweep(nullptr, nullptr, false);
             A = 0;
         }
-        if (d.flags & kSegDone) break;
+        if (flags & kSegDone) break;
     }
 }
 
@@ -378,6 +453,10 @@ int evrep_taf_stream_ordered(const uint32_t* t, const uint16_t* x, const uint16_
     tp.out_u8 = out_u8; tp.out_u8_stride = out_u8_stride;
     tp.emit_state = emit_state_every_window;
     tp.span = (float)((double)abin + 1e-8);
+    // four pixels per thread in the emission sweep: every tile starts on a multiple of 4 pixels (P is a multiple of 8),
+    // so rows are 16-byte (float) / 4-byte (uint8) aligned when the planes and window strides are
+    tp.vec_out = (((int64_t)H * W) % 4 == 0 && (!out || (out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)) &&
+                  (!out_u8 || (out_u8_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out_u8) & 3) == 0))) ? 1 : 0;
     if (ev_tiles_begin) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_begin), st));
     rc = K == 8 ? launch_taf_slices<8>(tp, st) : launch_taf_slices<4>(tp, st);
     if (rc) return rc;
