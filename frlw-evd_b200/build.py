@@ -38,7 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    extra = os.environ.get("EVREP_NVCC_EXTRA", "").split()       # e.g. -DEVREP_TAF_TIMING for tools/diag_taf_timing.py
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))

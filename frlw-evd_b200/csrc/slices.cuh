@@ -90,8 +90,9 @@ int prepare_slices(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
                    void* scratch, int64_t scratch_bytes, cudaStream_t st, SlicePlan& sp, SliceLayout& L);
 
 // ---- record feed of the tile kernels ------------------------------------------------------------
-// One producer warp per CTA walks the windows and bins of the plan, gathers the tile's run of every
-// slice of a bin with TMA bulk copies into a ring of stages in shared memory and hands the workers
+// The producer warps of a CTA walk the windows and bins of the plan (all of them the same way), gather the
+// tile's run of every slice of a bin with TMA bulk copies -- each warp its share of the runs -- into a ring
+// of stages in shared memory and hand the workers
 // one *segment* (the records of one bin, or a piece of it) per stage through a descriptor guarded by
 // mbarriers: FULL[stage] (transaction bytes + the producer's arrival), EMPTY[stage] (one arrival
 // per worker warp once it has read the records).
@@ -140,16 +141,17 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-constexpr int kFeedFullCount = 1;                  // FULL[stage]: the publisher's arrival (+ the TMA transaction bytes)
+constexpr int kFeedWarps = 4;                      // producer warps (one warpgroup): a bulk copy is issued lane by lane, so the runs of a bin are dealt out to four warps
+constexpr int kFeedFullCount = kFeedWarps;         // FULL[stage]: one arrival per producer warp (+ the TMA transaction bytes)
 
-// Producer side of the feed (one warp).  `seq` counts descriptors; stage = seq % kFeedStages.
+// Producer side of the feed (state of one producer warp).  `seq` counts descriptors; stage = seq % kFeedStages.
 struct FeedProducer {
     uint32_t* ring;
     SegDesc* desc;
     uint64_t* full;
     uint64_t* empty;
     uint32_t seq;
-    int lane;
+    int lane, pw;                // lane, and which of the kFeedWarps producer warps this is
 
     __device__ __forceinline__ void init(unsigned char* smem, const FeedSmem& fs) {
         ring = reinterpret_cast<uint32_t*>(smem + fs.ring);
@@ -158,15 +160,25 @@ struct FeedProducer {
         empty = reinterpret_cast<uint64_t*>(smem + fs.empty);
         seq = 0;
         lane = threadIdx.x & 31;
+        pw = (threadIdx.x >> 5) % kFeedWarps;
     }
     __device__ __forceinline__ int slot() const { return (int)(seq % kFeedStages); }
     // wait until the workers have drained the stage the next descriptor goes to
+#ifdef EVREP_TAF_TIMING
+    long long t_acquire = 0;
+    __device__ __forceinline__ void acquire() {
+        const long long t0 = clock64();
+        mbar_wait(empty + slot(), ((seq / kFeedStages) & 1u) ^ 1u);
+        t_acquire += clock64() - t0;
+    }
+#else
     __device__ __forceinline__ void acquire() { mbar_wait(empty + slot(), ((seq / kFeedStages) & 1u) ^ 1u); }
+#endif
     // publish the descriptor of the acquired stage (all copies into it have been issued)
     __device__ __forceinline__ void publish(uint32_t n_rec, uint32_t flags, uint32_t age_inc, uint32_t arg) {
         __syncwarp();
         if (lane == 0) {
-            desc[slot()] = SegDesc{n_rec, flags, age_inc, arg};
+            if (pw == 0) desc[slot()] = SegDesc{n_rec, flags, age_inc, arg};
             mbar_arrive(full + slot());
         }
         ++seq;
@@ -241,7 +253,7 @@ __device__ __forceinline__ bool FeedProducer::feed_bin(const SlicePlan& sp, uint
             if (!open) { acquire(); open = true; }
             const uint32_t se = sb + kFeedStageRecords;
             const uint32_t lo = start > sb ? start : sb, hi = end < se ? end : se;
-            if (lo < hi) {
+            if (lo < hi && (lane % kFeedWarps) == pw) {      // this warp's share of the runs
                 const uint32_t bytes = (hi - lo) * 4u;
                 mbar_add_tx(full + slot(), bytes);
                 tma_load_1d(ring + slot() * kFeedStageRecords + (lo - sb), src + (lo - start), bytes, full + slot());

@@ -24,7 +24,7 @@
 namespace evrep {
 
 constexpr int kTsWorkers = 256;                    // worker threads (8 warps)
-constexpr int kTsThreads = kTsWorkers + 32;        // + the producer warp
+constexpr int kTsThreads = kTsWorkers + 32 * kFeedWarps;   // + the producer warps
 constexpr int kTsWarps = kTsWorkers / 32;
 constexpr int kBarWorkers = 1;                     // named barrier of the worker warps
 constexpr uint32_t kCountShift = 23;               // packed accumulator: count in bits 23..31, sum of d below
@@ -69,6 +69,17 @@ __device__ __forceinline__ uint32_t leaky_u8_fast(float v) {
     return (uint32_t)(int)(fmaxf(r, 0.0f) * 255.0f);
 }
 
+#ifdef EVREP_TAF_TIMING
+// Diagnostic build only: cycles spent per tile CTA in [0] producer total, [1] producer waiting for a free stage,
+// [2] worker total, [3] worker waiting for a full stage, [4] worker barriers at bin ends, [5] sweeps, [6] accumulate, [7] push.
+__device__ unsigned long long g_taf_timing[kMaxSliceTiles][8];
+#define TAF_T0(v) const long long v = clock64()
+#define TAF_ADD(slot, v) do { t_acc[slot] += clock64() - (v); } while (0)
+#else
+#define TAF_T0(v) do {} while (0)
+#define TAF_ADD(slot, v) do {} while (0)
+#endif
+
 template <int K>
 __global__ void __launch_bounds__(kTsThreads, 2)
 taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
@@ -93,10 +104,13 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
     __syncthreads();
 
     if (tid >= kTsWorkers) {
-        // ================================== producer warp ==================================
+        // ================================== producer warps =================================
         FeedProducer fp;
         fp.init(smem_raw, fs);
         fp.open_row(sp, tile);
+#ifdef EVREP_TAF_TIMING
+        const long long p_start = clock64();
+#endif
         for (int w = 0; w < sp.n_windows; ++w) {
             if (w > 0 && sp.w_fresh[w]) fp.control(kSegReset, 0u, (uint32_t)w);
             const int g0 = sp.w_binbase[w], g1 = sp.w_binbase[w + 1];
@@ -119,6 +133,9 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
             }
             fp.control(kSegEmit | (w == sp.n_windows - 1 ? kSegDone : 0u), pend_age, (uint32_t)w);
         }
+#ifdef EVREP_TAF_TIMING
+        if (tid == kTsWorkers) { g_taf_timing[tile][0] = clock64() - p_start; g_taf_timing[tile][1] = fp.t_acquire; }
+#endif
         return;
     }
 
@@ -189,8 +206,18 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
         }
     };
 
-    // v = u - A for every cell, FIFO order restored, written to the window tensor / the uint8 file bytes / the state;
-    // u is rebased (u = v) in passing.  Four consecutive pixels per thread when the rows allow vector stores.
+    // Emission.  v = u - A for every cell, written back in FIFO order with the head reset to slot 0 (rebase + unrotate in
+    // place): the state array [K][2][P] then IS the tile's slice of the [2K,H,W] window tensor, channel 2e + p = row (e, p),
+    // and one thread sends it with 2K TMA bulk stores straight out of the state.  The rows must stay untouched until the
+    // copies have read them: `store_pending` makes the next push / sweep wait (thread 0, before the workers' barrier).
+    // The uint8 file bytes and the [H,W,2,K] state tensor are written by the threads themselves.
+    bool store_pending = false;
+    auto drain_stores = [&] {
+        if (store_pending) {
+            if (tid == 0) bulk_wait_read();
+            store_pending = false;
+        }
+    };
     auto sweep = [&](float* o, uint8_t* o8, bool write_state) {
         const float fa = (float)A;
         if (tp.vec_out) {
@@ -202,11 +229,6 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
                 const uint32_t addr = a_u + (uint32_t)c * 4u;
 #pragma unroll
                 for (int e = 0; e < K; ++e) r[e] = sld_v4f(addr + e * row_bytes);     // all loads in flight before the first use
-#pragma unroll
-                for (int e = 0; e < K; ++e) {
-                    r[e].x -= fa; r[e].y -= fa; r[e].z -= fa; r[e].w -= fa;
-                    sst_v4f(addr + e * row_bytes, r[e]);
-                }
                 // rotate each pixel's slots into FIFO order: position e = slot (head + e) mod K
                 float v[4][K];
 #pragma unroll
@@ -214,7 +236,7 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
                     const uint32_t h = (h4 >> (8 * j)) & 0xFFu;
                     float a[K];
 #pragma unroll
-                    for (int e = 0; e < K; ++e) a[e] = j == 0 ? r[e].x : j == 1 ? r[e].y : j == 2 ? r[e].z : r[e].w;
+                    for (int e = 0; e < K; ++e) a[e] = (j == 0 ? r[e].x : j == 1 ? r[e].y : j == 2 ? r[e].z : r[e].w) - fa;
 #pragma unroll
                     for (int sh = 1; sh < K; sh <<= 1) {
                         const bool on = (h & (uint32_t)sh) != 0u;
@@ -227,12 +249,9 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
 #pragma unroll
                     for (int e = 0; e < K; ++e) v[j][e] = a[e];
                 }
-                if (o) {
-                    float* row = o + (int64_t)p * HW + pix;
+                if (h4) sst_u32(a_head + c, 0u);
 #pragma unroll
-                    for (int e = 0; e < K; ++e, row += 2 * HW)
-                        __stcs(reinterpret_cast<float4*>(row), make_float4(v[0][e], v[1][e], v[2][e], v[3][e]));
-                }
+                for (int e = 0; e < K; ++e) sst_v4f(addr + e * row_bytes, make_float4(v[0][e], v[1][e], v[2][e], v[3][e]));
                 if (o8) {
                     // [K,2,H,W] with slot 0 = newest bin (np.flip of the [K,2,H,W] view)
                     uint8_t* row = o8 + ((int64_t)(K - 1) * 2 + p) * HW + pix;
@@ -252,6 +271,19 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
                     }
                 }
             }
+            if (o) {
+                fence_async_smem();                          // the rewritten rows, before the bulk copies read them
+                worker_sync();
+                if (tid == 0) {
+#pragma unroll
+                    for (int e = 0; e < K; ++e)
+#pragma unroll
+                        for (int p = 0; p < 2; ++p)
+                            bulk_store_1d(o + (int64_t)(2 * e + p) * HW, smem_raw + lay.state + (size_t)(e * C + p * P) * 4, (uint32_t)npix * 4u);
+                    bulk_commit();
+                }
+                store_pending = true;
+            }
             return;
         }
         for (int c = tid; c < C; c += kTsWorkers) {
@@ -260,11 +292,10 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
             const uint32_t h = sld_u8(a_head + c);
             float v[K];
 #pragma unroll
-            for (int e = 0; e < K; ++e) {
-                const uint32_t addr = a_u + ((h + e) & (K - 1)) * row_bytes + (uint32_t)c * 4u;
-                v[e] = __uint_as_float(sld_u32(addr)) - fa;
-                sst_f32(addr, v[e]);
-            }
+            for (int e = 0; e < K; ++e) v[e] = __uint_as_float(sld_u32(a_u + ((h + e) & (K - 1)) * row_bytes + (uint32_t)c * 4u)) - fa;
+            sst_u8(a_head + c, 0u);
+#pragma unroll
+            for (int e = 0; e < K; ++e) sst_f32(a_u + e * row_bytes + (uint32_t)c * 4u, v[e]);
             if (o) {
 #pragma unroll
                 for (int e = 0; e < K; ++e) __stcs(o + (int64_t)(2 * e + p) * HW + pix, v[e]);
@@ -281,13 +312,57 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
         }
     };
 
+#ifdef EVREP_TAF_TIMING
+    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long w_start = clock64();
+#endif
+    // The push of a bin is software-pipelined behind the accumulation of the next one: after the barrier that closes bin b
+    // the threads first fire the atomics of bin b + 1 (other accumulator buffer), then visit the cells of bin b again.
+    bool push_pending = false;
+    bool pend_scan = false;                              // the pending bin had more segments than a thread holds: scan instead
+    float pend_fa = 0.0f;
+    uint32_t pend[kHeldSegments * kPerSeg];
+#pragma unroll
+    for (int i = 0; i < kHeldSegments * kPerSeg; ++i) pend[i] = kNullRecord;
+    auto flush_push = [&] {
+        if (!push_pending) return;
+        TAF_T0(tp_);
+        // acc_alt is the pending bin's buffer (the buffers were swapped when it closed)
+        if (!pend_scan) {
+            // whoever exchanges a cell's word first gets its content and pushes; later visitors read zero
+            uint32_t xw[kHeldSegments * kPerSeg];
+#pragma unroll
+            for (int i = 0; i < kHeldSegments * kPerSeg; ++i)
+                xw[i] = pend[i] != kNullRecord ? satom_exch(acc_alt + (pend[i] & 0x3FFFu) * 4u, 0u) : 0u;
+#pragma unroll
+            for (int i = 0; i < kHeldSegments * kPerSeg; ++i)
+                if (xw[i]) push_cell(pend[i] & 0x3FFFu, xw[i] >> kCountShift, xw[i] & kSumMask, pend_fa);
+        } else {
+            for (int c = tid; c < C; c += kTsWorkers) {
+                const uint32_t xw = sld_u32(acc_alt + c * 4u);
+                if (xw) { sst_u32(acc_alt + c * 4u, 0u); push_cell((uint32_t)c, xw >> kCountShift, xw & kSumMask, pend_fa); }
+            }
+        }
+        push_pending = false;
+        dirty = true;
+        TAF_ADD(7, tp_);
+    };
+    // everything that sweeps the state first completes the pending push and waits for everybody's pushes and bulk stores
+    auto quiesce = [&] {
+        flush_push();
+        if (store_pending) { drain_stores(); dirty = true; }
+        if (dirty) { worker_sync(); dirty = false; }
+    };
+
     for (uint32_t seq = 0;; ++seq) {
         const uint32_t slot = seq % kFeedStages;
+        TAF_T0(tw);
         mbar_wait(full + slot, (seq / kFeedStages) & 1u);
+        TAF_ADD(3, tw);
         const uint4 dd = sld_v4(a_desc + slot * 16u);
         const uint32_t n_rec = dd.x, flags = dd.y, age_inc = dd.z, arg = dd.w;
         if (flags & kSegReset) {
-            if (dirty) { worker_sync(); dirty = false; }
+            quiesce();
             for (int c = tid; c < C; c += kTsWorkers) {
                 sst_u8(a_head + c, 0u);
 #pragma unroll
@@ -296,6 +371,7 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
             A = 0;
         }
         const bool wide = (flags & kSegWide) != 0;         // offsets beyond the packed word: the bin takes the exact path
+        TAF_T0(ta);
         if (n_rec && !wide) {
             // one packed atomic per record; the records stay in registers so that the push can visit their cells again
             const uint32_t recs = a_ring + slot * (kFeedStageRecords * 4u) + (uint32_t)tid * 4u;
@@ -320,32 +396,25 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);           // this warp is done with the stage
+        TAF_ADD(6, ta);
+        flush_push();                                        // the previous bin, behind this segment's atomics
         A += (int)age_inc;
         if (flags & kSegBinEnd) {
+            TAF_T0(tb);
+            drain_stores();                                  // the window tensor has left the state rows
             worker_sync();                                   // the bin is accumulated; earlier pushes are complete
+            dirty = false;
+            TAF_ADD(4, tb);
             const float fa = (float)(A - 1);
             const uint32_t hot_now = sld_u32(hot_cur);
             const bool exact = wide || hot_now != hot_seen_cur;
             hot_seen_cur = hot_now;
             if (!exact) {
-                if (seg_in_bin <= kHeldSegments) {
-                    // whoever exchanges a cell's word first gets its content and pushes; later visitors read zero
+                push_pending = true;
+                pend_scan = seg_in_bin > kHeldSegments;
+                pend_fa = fa;
 #pragma unroll
-                    for (int i = 0; i < kHeldSegments * kPerSeg; ++i) {
-                        if (held[i] != kNullRecord) {
-                            const uint32_t cell = held[i] & 0x3FFFu;
-                            const uint32_t xw = satom_exch(acc_cur + cell * 4u, 0u);
-                            if (xw) push_cell(cell, xw >> kCountShift, xw & kSumMask, fa);
-                        }
-                    }
-                } else {
-                    // a bin of more than two segments: scan the tile's accumulators instead
-                    for (int c = tid; c < C; c += kTsWorkers) {
-                        const uint32_t xw = sld_u32(acc_cur + c * 4u);
-                        if (xw) { sst_u32(acc_cur + c * 4u, 0u); push_cell((uint32_t)c, xw >> kCountShift, xw & kSumMask, fa); }
-                    }
-                }
-                dirty = true;
+                for (int i = 0; i < kHeldSegments * kPerSeg; ++i) pend[i] = held[i];
                 { const uint32_t t = acc_cur; acc_cur = acc_alt; acc_alt = t; }
                 { const uint32_t t = hot_cur; hot_cur = hot_alt; hot_alt = t; }
                 { const uint32_t t = hot_seen_cur; hot_seen_cur = hot_seen_alt; hot_seen_alt = t; }
@@ -373,28 +442,36 @@ taf_slice_tile_kernel(const __grid_constant__ TafSliceParams tp) {
                     }
                 }
                 worker_sync();
-                dirty = false;
             }
 #pragma unroll
             for (int i = 0; i < kHeldSegments * kPerSeg; ++i) held[i] = kNullRecord;
             seg_in_bin = 0;
         }
         if (flags & kSegEmit) {
-            if (dirty) { worker_sync(); dirty = false; }
+            quiesce();
             const bool last = (flags & kSegDone) != 0;
             // every emission rebases (u = v, A = 0): the state after a window does not depend on how the
             // windows are split over launches, so split launches == one launch, bit for bit
             float* o = tp.out ? tp.out + (int64_t)arg * tp.out_stride + pix0 : nullptr;
             uint8_t* o8 = tp.out_u8 ? tp.out_u8 + (int64_t)arg * tp.out_u8_stride + pix0 : nullptr;
+            TAF_T0(ts);
             sweep(o, o8, tp.emit_state || last);
+            TAF_ADD(5, ts);
             A = 0;
         } else if (A >= kRebaseAlways) {
-            if (dirty) { worker_sync(); dirty = false; }
+            quiesce();
             sweep(nullptr, nullptr, false);
             A = 0;
         }
         if (flags & kSegDone) break;
     }
+    if (tid == 0) bulk_wait_all();                           // shared memory must outlive the bulk reads
+#ifdef EVREP_TAF_TIMING
+    if (tid == 0) {
+        g_taf_timing[tile][2] = clock64() - w_start;
+        for (int i = 3; i < 8; ++i) g_taf_timing[tile][i] = t_acc[i];
+    }
+#endif
 }
 
 template <int K>
@@ -470,5 +547,13 @@ int evrep_stream_order_violations(const void* scratch, uint32_t* host_out, evrep
     EVREP_CUDA(cudaStreamSynchronize(as_stream(stream)));
     return EVREP_OK;
 }
+
+#ifdef EVREP_TAF_TIMING
+int evrep_debug_taf_timing(unsigned long long* host, int n_tiles) {
+    EVREP_CUDA(cudaDeviceSynchronize());
+    EVREP_CUDA(cudaMemcpyFromSymbol(host, g_taf_timing, sizeof(unsigned long long) * 8 * (size_t)n_tiles));
+    return EVREP_OK;
+}
+#endif
 
 }  // extern "C"
