@@ -132,7 +132,7 @@ class HostPipeline:
         dev = self.device
         self.raw = [torch.empty(max(max_ev, 1) * 8, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.soa = [ops.EventStream.empty(max(max_ev, 1), dev) for _ in range(2)]
-        self.assume_ordered = os.environ.get("EVREP_TAF_PATH", "") != "bucketed"
+        self.assume_ordered = os.environ.get("EVREP_TAF_PATH", "") == "ordered"
         self.fused_u8 = self.assume_ordered and tuple(geom.grid) == tuple(geom.target)
         self.vol = None if self.fused_u8 else torch.empty((max(max_w, 1), 2 * K, H, W), dtype=torch.float32, device=dev)
         self.violations = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -190,7 +190,8 @@ class HostPipeline:
 
     def order_violations(self) -> int:
         """Events found outside the bin their position implies, over all runs so far (synchronises).
-        Non-zero means the payload was not ordered in time: run again with ``EVREP_TAF_PATH=bucketed``."""
+        Only the ``EVREP_TAF_PATH=ordered`` kernels count them; non-zero means the payload was not ordered in
+        time and the run has to be repeated on the default path."""
         return int(self.violations.item())
 
 

@@ -331,9 +331,11 @@ def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=N
     slot flip, ``generate_taf.py:226-235``) straight from the tile kernel.  ``tile_events``:
     optional pair of ``torch.cuda.Event(enable_timing=True)`` recorded around the tile kernel.
 
-    Time-ordered streams (``ev.is_ordered()``) take the one-pass slice sort
-    (``evrep_taf_stream_ordered``); anything else the general two-pass bucketing
-    (``evrep_taf_stream``).  ``EVREP_TAF_PATH=bucketed`` forces the latter."""
+    Two implementations with the same results: the general two-pass bucketing + register-resident
+    tile kernel (``evrep_taf_stream``, the default: the faster one on every BASELINE configuration,
+    see DESIGN.md section 4.1e), and, with ``EVREP_TAF_PATH=ordered`` and a time-ordered stream
+    (``ev.is_ordered()``), the one-pass slice sort + shared-memory tile kernel
+    (``evrep_taf_stream_ordered``), which can also write the uint8 file bytes itself."""
     _need_cuda(ev.t, state)
     H, W = shape
     nw = len(windows)
@@ -348,7 +350,7 @@ def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=N
     xm, ym = _maps(maps)
     sensor = maps.sensor_shape if maps is not None else (H, W)
     lib = _lib.load()
-    ordered = os.environ.get("EVREP_TAF_PATH", "") != "bucketed" and ev.is_ordered()
+    ordered = os.environ.get("EVREP_TAF_PATH", "") == "ordered" and ev.is_ordered()
     if ordered:
         need = lib.evrep_taf_stream_ordered_scratch_bytes(ev.n, nw, total_bins, H, W, K)
         if need < 0:

@@ -1,5 +1,5 @@
-"""The time-ordered TAF path (slice sort + shared-memory tile kernel, `evrep_taf_stream_ordered`)
-against the oracle and against the general two-pass path: hot pixels (exact two-word
+"""The time-ordered TAF path (slice sort + shared-memory tile kernel, `evrep_taf_stream_ordered`,
+selected with EVREP_TAF_PATH=ordered) against the oracle and against the default two-pass path: hot pixels (exact two-word
 accumulators), wide offsets, bins of many slices, the native 1MP grid (several waves of tiles),
 K = 4 under the gen4 policy, the in-kernel uint8 output and the order check.
 Float tolerance 1e-5 rel / 1e-6 abs (BASELINE.json north_star)."""
@@ -26,14 +26,13 @@ def idx(t, v):
 
 def both_paths(monkeypatch, ev, windows, abin, grid, K, maps=None):
     """(ordered result, ordered state, bucketed result, bucketed state)."""
-    monkeypatch.delenv("EVREP_TAF_PATH", raising=False)
+    monkeypatch.setenv("EVREP_TAF_PATH", "ordered")
     s1 = ops.taf_fresh_state(grid, K, DEV)
     a = ops.taf_stream(ev, windows, abin, grid, K, s1, maps)
     assert ops.order_violations(DEV) == 0
-    monkeypatch.setenv("EVREP_TAF_PATH", "bucketed")
+    monkeypatch.delenv("EVREP_TAF_PATH", raising=False)
     s2 = ops.taf_fresh_state(grid, K, DEV)
     b = ops.taf_stream(ev, windows, abin, grid, K, s2, maps)
-    monkeypatch.delenv("EVREP_TAF_PATH", raising=False)
     return a, s1, b, s2
 
 
@@ -57,6 +56,7 @@ def test_hot_pixel_takes_the_exact_path(monkeypatch):
     got, state, old, _ = both_paths(monkeypatch, ev, windows, abin, (H, W), K)
     for i in range(2):
         assert close(got[i], want[i]), i
+        assert close(old[i], want[i]), i                 # the default path on the same hot pixel
     assert close(state, want_state)
     # the hot cell itself: mean of 20000 offsets; the reference sums float32 sequentially, the kernel sums integers
     cell = got[0][2 * (K - 1) + 1, 33, 17].item()
@@ -105,10 +105,17 @@ def test_bin_of_many_slices(monkeypatch):
     assert close(state, want_state)
 
 
+@pytest.fixture
+def ordered_path(monkeypatch):
+    monkeypatch.setenv("EVREP_TAF_PATH", "ordered")
+
+
+@pytest.mark.parametrize("path", ["ordered", "bucketed"])
 @pytest.mark.parametrize("K", [8, 4])
-def test_native_1mp_grid_against_oracle(K):
+def test_native_1mp_grid_against_oracle(K, path, monkeypatch):
     """720 x 1280 without down-scaling: more tiles than resident CTAs (several waves), a fresh window
     and two incremental ones."""
+    monkeypatch.setenv("EVREP_TAF_PATH", path)
     H, W, abin = 720, 1280, 10000
     t, x, y, p = synth.make_stream(H, W, 70000, 2e7, 31)
     windows = [(0, idx(t, 30000), 0, 3, 1), (idx(t, 30000), idx(t, 50000), 30000, 2, 0), (idx(t, 50000), idx(t, 70000), 50000, 2, 0)]
@@ -122,8 +129,10 @@ def test_native_1mp_grid_against_oracle(K):
     assert close(state, want_state)
 
 
-def test_k4_gen4_policy_against_oracle():
+@pytest.mark.parametrize("path", ["ordered", "bucketed"])
+def test_k4_gen4_policy_against_oracle(path, monkeypatch):
     """K = 4 on the down-scaled 512 x 640 grid (gen4 policy: float64 scale, truncation)."""
+    monkeypatch.setenv("EVREP_TAF_PATH", path)
     t, x, y, p = synth.make_stream(720, 1280, 80000, 1e7, 41)
     windows = [(0, idx(t, 40000), 0, 4, 1), (idx(t, 40000), idx(t, 80000), 40000, 4, 0)]
     want, want_state = oracle_taf_windows(t, x, y, p, windows, 10000, (512, 640), 4, scale=(640 / 1280, 512 / 720))
@@ -136,7 +145,7 @@ def test_k4_gen4_policy_against_oracle():
     assert close(state, want_state)
 
 
-def test_uint8_straight_from_the_tile_kernel():
+def test_uint8_straight_from_the_tile_kernel(ordered_path):
     """out_u8 against the fused epilogue applied to the float tensors of the same call (within one step on
     fewer than 0.1 % of the bytes); also without any float output at all."""
     t, x, y, p = synth.make_stream(720, 1280, 100000, 1e7, 51)
@@ -157,7 +166,7 @@ def test_uint8_straight_from_the_tile_kernel():
     assert torch.equal(u8, u8b) and torch.equal(state, state2)
 
 
-def test_unordered_input_is_detected_and_routed(monkeypatch):
+def test_unordered_input_is_detected_and_routed(ordered_path):
     """A stream with a few timestamps out of order: `is_ordered` sends it to the general path (oracle
     parity); forcing it through the ordered entry point reports the violations."""
     H, W, K, abin = 24, 40, 8, 1000
@@ -179,7 +188,7 @@ def test_unordered_input_is_detected_and_routed(monkeypatch):
     assert ops.order_violations(DEV) > 0
 
 
-def test_long_window_rebases_inside():
+def test_long_window_rebases_inside(ordered_path):
     """One fresh window of 100 non-empty bins: the lazy ageing counter is folded back every 8 bins."""
     H, W, K, abin = 24, 40, 8, 1000
     rng = np.random.Generator(np.random.PCG64(17))
