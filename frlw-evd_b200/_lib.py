@@ -27,6 +27,16 @@ class EvWindow(ctypes.Structure):
     _fields_ = [("ev_begin", c_int64), ("ev_end", c_int64), ("t0", c_int64)]
 
 
+class EvSegment(ctypes.Structure):
+    """``evrep_ev_segment`` (include/evrep.h)."""
+    _fields_ = [("ev_begin", c_int64), ("ev_end", c_int64), ("start_time", c_int64)]
+
+
+class EvSpan(ctypes.Structure):
+    """``evrep_ev_span`` (include/evrep.h)."""
+    _fields_ = [("first_segment", c_int32), ("last_segment", c_int32), ("t0", c_int64), ("tw", c_int64)]
+
+
 class CountSegment(ctypes.Structure):
     """``evrep_count_segment`` (include/evrep.h)."""
     _fields_ = [("ev_begin", c_int64), ("ev_end", c_int64)]
@@ -75,6 +85,10 @@ SIGNATURES = {
     "evrep_event_volume_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "evrep_event_volume_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int64, c_int, c_int, c_int, P, P, c_int, c_int,
                                           P, c_int64, P, c_int64, P]),
+    "evrep_event_volume_spans_scratch_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int, c_int]),
+    "evrep_event_volume_spans": (c_int, [P, P, P, P, c_int64, P, c_int, P, c_int, c_int, c_int, c_int, P, P, c_int, c_int,
+                                         P, c_int64, P, c_int64, P, c_int64, P, P, P]),
+    "evrep_event_volume_u8_batch": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "evrep_count_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
     "evrep_count_stream": (c_int, [P, P, P, P, c_int64, P, c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int64,
                                    P, c_int64, P]),

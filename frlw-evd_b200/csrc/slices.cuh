@@ -196,9 +196,13 @@ struct FeedProducer {
     __device__ __forceinline__ void open_row(const SlicePlan& sp, int tile) {
         row = sp.runs + (int64_t)tile * sp.pitch;
         n_slices = sp.status[1];
-        win_base = 0;
-        win_lo = lane < n_slices ? __ldg(row + lane) : 0u;
-        win_hi = 32u + lane < n_slices ? __ldg(row + 32 + lane) : 0u;
+        rewind(0u);
+    }
+    // The window only slides forward; a reader that goes back (overlapping Event Volume spans) opens it again.
+    __device__ __forceinline__ void rewind(uint32_t slice) {
+        win_base = slice & ~31u;
+        win_lo = win_base + lane < n_slices ? __ldg(row + win_base + lane) : 0u;
+        win_hi = win_base + 32u + lane < n_slices ? __ldg(row + win_base + 32 + lane) : 0u;
     }
     // Entry of slice s0 + lane (0 beyond the window's reach or `count`): slices s0 .. s0 + 31 must start inside the window.
     __device__ __forceinline__ uint32_t entries(uint32_t s0, uint32_t count) {
@@ -213,11 +217,14 @@ struct FeedProducer {
         return lane < count ? (k < 32u ? from_lo : from_hi) : 0u;
     }
     // All records of this tile in bin `gbin` -> one or more segments; returns false when the tile has none.
-    __device__ bool feed_bin(const SlicePlan& sp, uint32_t gbin, uint32_t first_slice, uint32_t parts, uint32_t dyn, uint32_t age_inc);
+    // `age_inc` goes into the descriptor of the bin's last segment, or of every segment (`age_on_all`, the Event Volume
+    // kernel keeps a time offset there).
+    __device__ bool feed_bin(const SlicePlan& sp, uint32_t gbin, uint32_t first_slice, uint32_t parts, uint32_t dyn, uint32_t age_inc,
+                             bool age_on_all = false);
 };
 
 __device__ __forceinline__ bool FeedProducer::feed_bin(const SlicePlan& sp, uint32_t gbin, uint32_t first_slice, uint32_t parts,
-                                                       uint32_t dyn, uint32_t age_inc) {
+                                                       uint32_t dyn, uint32_t age_inc, bool age_on_all) {
     const uint32_t wide = (dyn & kBinBigD) ? kSegWide : 0u;
     // pass 1 (bins of more than 32 slices only): the bin's total, so that the last segment is known when it is built
     uint32_t total = 0;
@@ -260,7 +267,7 @@ __device__ __forceinline__ bool FeedProducer::feed_bin(const SlicePlan& sp, uint
             }
             if (q1 >= se || q1 == total) {              // the stage is complete: full, or the bin ends in it
                 const bool last = (se >= total);
-                publish((last ? total : se) - sb, wide | (last ? kSegBinEnd : 0u), last ? age_inc : 0u, gbin);
+                publish((last ? total : se) - sb, wide | (last ? kSegBinEnd : 0u), (last || age_on_all) ? age_inc : 0u, gbin);
                 open = false;
             }
         }

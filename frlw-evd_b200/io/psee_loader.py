@@ -133,6 +133,10 @@ class PSEELoader(object):
         self.done = self._pos >= self._ev_count
         return lo, hi
 
+    def lower_index(self, time_us, lo, hi):
+        """First index in ``[lo, hi)`` whose timestamp is ``>= time_us``."""
+        return bisect.bisect_left(self._t, time_us, lo, hi)
+
     def upper_index(self, time_us, lo, hi):
         """First index in ``[lo, hi)`` whose timestamp is ``> time_us`` (the drivers'
         ``events[:, 2] > bound`` filters on time-sorted slices)."""

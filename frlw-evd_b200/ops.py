@@ -488,6 +488,95 @@ def event_volume_stream(ev: EventStream, windows, tw: int, shape, K: int, maps=N
     return out
 
 
+EV_SEGMENT_MAX_US = 262000      # a record keeps an 18-bit offset from its segment's start
+
+
+def plan_ev_spans(windows, time_of, lower_index):
+    """Host-side plan of ``event_volume_spans``.  ``windows``: ``(ev_begin, ev_end, t0, tw)`` in any
+    order, free to overlap and nest (``generate_eventvolume.py:118-147``).  ``time_of(i)``: timestamp of
+    event ``i``; ``lower_index(T, lo, hi)``: first index in ``[lo, hi)`` with ``t >= T`` (both on the
+    host, e.g. ``PSEELoader.time_of`` / ``lower_index``).  The stream is cut at every window boundary,
+    and wherever a piece would span more than ``EV_SEGMENT_MAX_US``; pieces no window covers are
+    left out.  Returns ``(segments [(ev_begin, ev_end, start_time)], spans [(first, last, t0, tw)])``."""
+    marks = {}
+    for a, b, _t0, _tw in windows:
+        if b > a:
+            marks[int(a)] = marks.get(int(a), 0) + 1
+            marks[int(b)] = marks.get(int(b), 0) - 1
+    cuts = sorted(marks)
+    segments, first_at, last_at = [], {}, {}
+    cover = 0
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        cover += marks[lo]
+        if cover <= 0:
+            continue
+        first_at[lo] = len(segments)
+        while True:
+            start = int(time_of(lo))
+            if int(time_of(hi - 1)) - start <= EV_SEGMENT_MAX_US:
+                break
+            cut = int(lower_index(start + EV_SEGMENT_MAX_US, lo, hi))      # > lo: t[lo] = start < start + max
+            segments.append((lo, cut, start))
+            lo = cut
+        segments.append((lo, hi, start))
+        last_at[hi] = len(segments) - 1
+    spans = []
+    for a, b, t0, tw in windows:
+        if b > a:
+            spans.append((first_at[int(a)], last_at[int(b)], int(t0), int(tw)))
+        else:
+            spans.append((0, -1, int(t0), int(tw)))
+    return segments, spans
+
+
+def event_volume_spans(ev: EventStream, segments, spans, shape, K: int, maps=None, out=None, out_u8=None,
+                       want_f32=True, tile_events=None):
+    """V2 for overlapping / nested windows on a time-ordered stream (``evrep_event_volume_spans``): the
+    events are sorted once by (segment, sensor tile), every span splats the records of its segments with
+    its own ``(t - t0) / tw``.  ``segments`` / ``spans`` as returned by ``plan_ev_spans``.  Returns f32
+    ``[n_spans, 2K, H, W]`` (``None`` with ``want_f32=False``); ``out_u8``: optional u8 tensor of the
+    same shape that receives the file bytes (clamp at 255, truncation) when no resize follows."""
+    _need_cuda(ev.t)
+    H, W = shape
+    ns, nsp = len(segments), len(spans)
+    seg_arr = (_lib.EvSegment * max(ns, 1))()
+    for i, g in enumerate(segments):
+        seg_arr[i] = _lib.EvSegment(int(g[0]), int(g[1]), int(g[2]))
+    span_arr = (_lib.EvSpan * max(nsp, 1))()
+    for i, sp in enumerate(spans):
+        span_arr[i] = _lib.EvSpan(int(sp[0]), int(sp[1]), int(sp[2]), int(sp[3]))
+    if out is None and want_f32:
+        out = torch.empty((nsp, 2 * K, H, W), dtype=torch.float32, device=ev.device)
+    need = _lib.load().evrep_event_volume_spans_scratch_bytes(ev.n, ns, nsp, H, W, K)
+    if need < 0:
+        _lib.check(int(need), "evrep_event_volume_spans_scratch_bytes")
+    buf = workspace("ev_spans", need, ev.device)
+    xm, ym = _maps(maps)
+    sensor = maps.sensor_shape if maps is not None else (H, W)
+    _lib.call("evrep_event_volume_spans", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+              ctypes.cast(seg_arr, ctypes.c_void_p), ns, ctypes.cast(span_arr, ctypes.c_void_p), nsp, H, W, K, xm, ym,
+              sensor[0], sensor[1], _ptr(out), 2 * K * H * W, _ptr(out_u8), 2 * K * H * W, _ptr(buf), buf.numel(),
+              _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
+    return out
+
+
+def event_volume_u8_batch(volumes, target_shape=None, maps=None, out=None):
+    """f32 ``[n,C,H,W]`` -> u8 ``[n,C,Ht,Wt]``: optional nearest resize (gen1 policy), clamp at 255,
+    truncation (``generate_eventvolume.py:150-160`` for a batch of windows)."""
+    _need_cuda(volumes)
+    n, C, H, W = volumes.shape
+    assert volumes.is_contiguous()
+    Ht, Wt = target_shape if target_shape is not None else (H, W)
+    if (Ht, Wt) != (H, W) and maps is None:
+        maps = nearest_maps((H, W), (Ht, Wt), volumes.device)
+    ys, xs = maps if (maps is not None and (Ht, Wt) != (H, W)) else (None, None)
+    if out is None:
+        out = torch.empty((n, C, Ht, Wt), dtype=torch.uint8, device=volumes.device)
+    _lib.call("evrep_event_volume_u8_batch", _ptr(volumes), C * H * W, n, C, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
+              _stream(volumes.device))
+    return out
+
+
 def timesurface(ev: EventStream, shape):
     """Time-surface pair of ``generate_opticalflow.py:72-92`` on a SoA slice: ``(f64 [H,W] last
     timestamp older than newest - 50000, f64 [H,W] last timestamp)``, shifted, scaled and clamped

@@ -108,13 +108,16 @@ class AsyncWriter:
         self._dirs = set()
         self.bytes_written = 0
 
-    def put(self, array: np.ndarray, *path) -> None:
+    def put(self, array: np.ndarray, *path):
+        """Queue one file; returns its future (the array must stay untouched until it is done)."""
         folder = os.path.join(*path[:-1])
         if folder not in self._dirs:
             os.makedirs(folder, exist_ok=True)
             self._dirs.add(folder)
         self.bytes_written += array.nbytes
-        self._pending.append(self._pool.submit(array.tofile, os.path.join(*path)))
+        future = self._pool.submit(array.tofile, os.path.join(*path))
+        self._pending.append(future)
+        return future
 
     def drain(self) -> None:
         """Block until everything submitted so far is on disk (buffers may then be reused)."""
@@ -125,3 +128,61 @@ class AsyncWriter:
     def close(self) -> None:
         self.drain()
         self._pool.shutdown()
+
+
+class PinnedRing:
+    """Device -> host -> file hand-over of the drivers' output chunks without a blocking copy on the
+    encode loop and with a bounded amount of page-locked memory: a ring of pinned buffers, a copy
+    stream, and the ``AsyncWriter``.  ``push(dev_u8, emit)`` queues the device->host copy of a chunk
+    behind the kernels that produce it and returns at once; ``emit(host_array)`` -- which calls
+    ``writer.put`` for every file of the chunk and returns the futures -- runs when the NEXT chunk is
+    pushed (or at ``flush``), i.e. while the GPU is already encoding again.  A buffer is reused only
+    after its files are on disk."""
+
+    def __init__(self, device="cuda", slots: int = 3):
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.slots = [dict(buf=None, done=None, emit=None, futures=[], shape=None) for _ in range(slots)]
+        self.count = 0
+        self.pinned_bytes = 0
+
+    def _retire(self, slot):
+        if slot["emit"] is not None:
+            slot["done"].synchronize()
+            n = int(np.prod(slot["shape"]))
+            slot["futures"] = list(slot["emit"](slot["buf"][:n].numpy().reshape(slot["shape"])) or [])
+            slot["emit"] = None
+
+    def push(self, dev_u8: torch.Tensor, emit) -> None:
+        assert dev_u8.dtype == torch.uint8 and dev_u8.is_contiguous()
+        if self.count:
+            self._retire(self.slots[(self.count - 1) % len(self.slots)])      # the previous chunk has had a whole encode to land
+        slot = self.slots[self.count % len(self.slots)]
+        self._retire(slot)
+        for f in slot["futures"]:
+            f.result()                                                        # its files are written: the buffer is free
+        slot["futures"] = []
+        n = dev_u8.numel()
+        if slot["buf"] is None or slot["buf"].numel() < n:
+            self.pinned_bytes += n - (0 if slot["buf"] is None else slot["buf"].numel())
+            slot["buf"] = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        self.copy_stream.wait_event(ready)
+        with torch.cuda.stream(self.copy_stream):
+            slot["buf"][:n].copy_(dev_u8.view(-1), non_blocking=True)
+            dev_u8.record_stream(self.copy_stream)
+            slot["done"] = torch.cuda.Event()
+            slot["done"].record(self.copy_stream)
+        slot["emit"], slot["shape"] = emit, tuple(dev_u8.shape)
+        self.count += 1
+
+    def flush(self) -> None:
+        """Hand every chunk still in flight to the writer and wait for the files."""
+        for k in range(len(self.slots)):
+            slot = self.slots[(self.count + k) % len(self.slots)]
+            self._retire(slot)
+        for slot in self.slots:
+            for f in slot["futures"]:
+                f.result()
+            slot["futures"] = []

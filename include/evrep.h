@@ -250,6 +250,46 @@ int evrep_event_volume_stream(const uint32_t* t, const uint16_t* x, const uint16
                               float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
                               evrep_stream_t stream);
 
+/* -------------------- V2 (time-ordered input): Event Volume for overlapping, nested windows ------
+ * generate_eventvolume.py:118-169 encodes, for every label, the events of the last 250 / 500 /
+ * 1000 ms: windows that nest inside a label and overlap between labels.  The caller cuts the
+ * stream at every window boundary into consecutive segments -- events [ev_begin, ev_end), all of
+ * them with start_time <= t < start_time + 262144 -- and gives every window ("span") as a run of
+ * segments first_segment .. last_segment (inclusive; first > last = no events) with its own origin
+ * t0 and length tw: t_norm = (t - t0) / tw in float64 (:141).  The events are sorted once by
+ * (segment, sensor tile) with the one-pass slice sort of evrep_taf_stream_ordered; every span
+ * then re-reads the 4-byte records of its segments and splats them with its own normalisation
+ * (shared-memory fixed-point accumulators as in evrep_event_volume_stream, one CTA per tile).
+ * No limit on tw below 2^31 us.  Timestamps must be non-decreasing over the segments.
+ * out (nullable): f32 [n_spans][2K,H,W], values / 5 * 255 (:37).  out_u8 (nullable): u8
+ * [n_spans][2K,H,W], the file bytes when no resize follows (clamped at 255, truncated, :158-160).
+ * evrep_event_volume_u8_batch turns a batch of float volumes into those bytes with the optional
+ * nearest resize of the gen1 policy (:150). */
+typedef struct {
+    int64_t ev_begin;
+    int64_t ev_end;
+    int64_t start_time;
+} evrep_ev_segment;
+
+typedef struct {
+    int32_t first_segment;
+    int32_t last_segment;
+    int64_t t0;
+    int64_t tw;
+} evrep_ev_span;
+
+int64_t evrep_event_volume_spans_scratch_bytes(int64_t n_events, int n_segments, int n_spans, int H, int W, int K);
+int evrep_event_volume_spans(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
+                             int64_t n_events, const evrep_ev_segment* segments_host, int n_segments,
+                             const evrep_ev_span* spans_host, int n_spans, int H, int W, int K,
+                             const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                             float* out, int64_t out_stride, uint8_t* out_u8, int64_t out_u8_stride,
+                             void* scratch, int64_t scratch_bytes,
+                             void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream);
+int evrep_event_volume_u8_batch(const float* volumes, int64_t volume_stride, int n, int C, int H, int W,
+                                int Ht, int Wt, const int32_t* ysrc, const int32_t* xsrc, uint8_t* out,
+                                evrep_stream_t stream);
+
 /* ------------------------------------------------- E1 + E2 over a whole stream -------
  * generate_eventcountimage.py:130-182 for many labels in one call.  The driver's windows (the
  * last N events before a label, several N per label) nest and overlap; the caller cuts the

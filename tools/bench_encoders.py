@@ -75,6 +75,18 @@ def main():
                timed(lambda: ops.event_volume_stream(ev, windows, 50000, (H, W), K, maps, outs), args.iters),
                9 * n + nw * 8 * K * HW, n)
 
+    # the same windows through the slice sort + span kernel (time-ordered streams; also serves nested windows)
+    import bisect
+    segments, spans = ops.plan_ev_spans([(lo, hi, t0, 50000) for lo, hi, t0 in windows], lambda i: int(t[i]),
+                                        lambda T, lo, hi: bisect.bisect_left(t, T, lo, hi))
+    for K in (5, 8):
+        outs = torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=dev)
+        pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ms = timed(lambda: ops.event_volume_spans(ev, segments, spans, (H, W), K, maps, outs, tile_events=pair), args.iters)
+        torch.cuda.synchronize()
+        report("event_volume_spans_K%d_50ms_windows" % K, ms, 9 * n + nw * 8 * K * HW, n,
+               {"tile_kernel_ms": pair[0].elapsed_time(pair[1])})
+
     def run_eci():
         for lo, hi, _ in windows:
             ops.count_image(ev.slice(lo, hi), (H, W), maps)
