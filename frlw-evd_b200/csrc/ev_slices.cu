@@ -17,7 +17,7 @@
 
 namespace evrep {
 
-constexpr int kEvsWorkers = 256;
+constexpr int kEvsWorkers = 512;
 constexpr int kEvsThreads = kEvsWorkers + 32 * kFeedWarps;
 constexpr int kEvsWarps = kEvsWorkers / 32;
 constexpr int kEvsBar = 1;
@@ -119,6 +119,8 @@ ev_slice_tile_kernel(const __grid_constant__ EvSliceParams tp) {
     for (uint32_t i = tid; i < ((uint32_t)rows * Pu + 3u) / 4u; i += kEvsWorkers) acc_hi[i] = 0u;
     worker_sync();
 
+    const uint32_t row_first = (uint32_t)tid / p4, c4_first = (uint32_t)tid - row_first * p4;
+    const uint32_t row_step = kEvsWorkers / p4, c4_step = kEvsWorkers - row_step * p4;
     const float Kf = (float)K;
     uint32_t cur_span = 0xFFFFFFFFu;
     double tw = 1.0, inv_tw = 1.0;
@@ -181,8 +183,10 @@ ev_slice_tile_kernel(const __grid_constant__ EvSliceParams tp) {
             };
             auto to_byte = [](float v) -> uint32_t { return (uint32_t)(int)fminf(v, 255.0f); };   // clamp, then astype(uint8)
             if (tp.vec_out) {
-                for (uint32_t i = tid; i < n4; i += kEvsWorkers) {
-                    const uint32_t row = i / p4, c4 = i - row * p4;
+                // thread walks the float4 cells i = tid + k * kEvsWorkers of the [2K][P] tile: (row, c4) advance without a division
+                uint32_t row = row_first, c4 = c4_first;
+                for (uint32_t i = tid; i < n4; i += kEvsWorkers, row += row_step, c4 += c4_step) {
+                    if (c4 >= p4) { c4 -= p4; ++row; }
                     const uint4 lo = reinterpret_cast<uint4*>(acc)[i];
                     const uint32_t wr = acc_hi[i];
                     if (lo.x | lo.y | lo.z | lo.w) reinterpret_cast<uint4*>(acc)[i] = make_uint4(0u, 0u, 0u, 0u);
