@@ -111,6 +111,11 @@ SIGNATURES = {
     "evrep_sparse_taf": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P]),
     "evrep_sparse_event_frame": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
     "evrep_sparse_to_dense": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
+    "evrep_compact_scratch_bytes": (c_int64, [c_int64]),
+    "evrep_dense_to_sparse": (c_int, [P, P, c_int, c_int, P, P, P, P, P]),
+    "evrep_event_memory_update": (c_int, [P, c_int64, P, c_int64, c_double, P, P, P, P, P]),
+    "evrep_taf_online_scratch_bytes": (c_int64, [c_int, c_int, c_int]),
+    "evrep_taf_online_bin": (c_int, [P, c_int64, c_double, c_double, c_double, c_int, c_int, c_int, c_int, P, P, P, P]),
     "evrep_event_queue_tensor": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
 }
 

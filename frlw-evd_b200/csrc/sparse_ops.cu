@@ -157,6 +157,208 @@ zero_f32_kernel(float* __restrict__ p, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0.0f;
 }
 
+
+// ---- stable row compaction (denseToSparse, the raw-event memory of generate_event_volume_cuda) -------------
+// Three small passes: flags + per-block counts, a scan of the block counts, then each block ranks its rows and
+// copies the kept ones -- the output keeps the input order, like torch.nonzero / boolean indexing do.
+constexpr int kCompactBlock = 256;
+constexpr int kCompactPerThread = 8;
+constexpr int kCompactRows = kCompactBlock * kCompactPerThread;
+
+// kind 0: a row of `cols` floats is kept when any element is non-zero (|.|-sum != 0, sparse_ops.py:131)
+// kind 1: a row of `cols` doubles is kept when column 3 >= thr                          (sparse_ops.py:42)
+template <int kKind>
+__device__ __forceinline__ bool keep_row(const void* src, int64_t row, int cols, double thr) {
+    if (kKind == 0) {
+        const float* r = reinterpret_cast<const float*>(src) + row * cols;
+        bool any = false;
+        for (int c = 0; c < cols; ++c) any |= (r[c] != 0.0f);
+        return any;
+    }
+    return reinterpret_cast<const double*>(src)[row * cols + 3] >= thr;
+}
+
+template <int kKind>
+__global__ void __launch_bounds__(kCompactBlock)
+compact_count_kernel(const void* __restrict__ src, int64_t n, int cols, double thr, uint32_t* __restrict__ block_counts) {
+    const int64_t base = (int64_t)blockIdx.x * kCompactRows;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kCompactPerThread; ++k) {
+        const int64_t row = base + (int64_t)threadIdx.x * kCompactPerThread + k;
+        if (row < n && keep_row<kKind>(src, row, cols, thr)) ++mine;
+    }
+    mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+    __shared__ uint32_t warp_sum[kCompactBlock / 32];
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < kCompactBlock / 32; ++w) total += warp_sum[w];
+        block_counts[blockIdx.x] = total;
+    }
+}
+
+// exclusive scan of the block counts in place (one CTA); total -> block_counts[n_blocks]
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(uint32_t* __restrict__ block_counts, int n_blocks) {
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? block_counts[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        uint32_t before = carry;
+        for (int k = 0; k < wid; ++k) before += warp_sum[k];
+        if (i < n_blocks) block_counts[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_counts[n_blocks] = carry;
+}
+
+// copies the kept rows (row_bytes each) to their ranks; optionally writes their unravelled index (spatial dims first,
+// batch last: sparse_ops.py:132) as int64 rows of `n_dims` entries.
+struct CompactDims { int64_t size[4]; int n; };
+
+template <int kKind>
+__global__ void __launch_bounds__(kCompactBlock)
+compact_scatter_kernel(const void* __restrict__ src, int64_t n, int cols, double thr, const uint32_t* __restrict__ block_offsets,
+                       void* __restrict__ dst, int64_t* __restrict__ locations, CompactDims dims) {
+    const int64_t base = (int64_t)blockIdx.x * kCompactRows;
+    bool keep[kCompactPerThread];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kCompactPerThread; ++k) {
+        const int64_t row = base + (int64_t)threadIdx.x * kCompactPerThread + k;
+        keep[k] = row < n && keep_row<kKind>(src, row, cols, thr);
+        mine += keep[k] ? 1u : 0u;
+    }
+    // exclusive scan of the per-thread counts over the block
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __shared__ uint32_t warp_sum[kCompactBlock / 32];
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    uint32_t rank = block_offsets[blockIdx.x] + incl - mine;
+    for (int k = 0; k < wid; ++k) rank += warp_sum[k];
+    const int elem = kKind == 0 ? 4 : 8;
+#pragma unroll
+    for (int k = 0; k < kCompactPerThread; ++k) {
+        if (!keep[k]) continue;
+        const int64_t row = base + (int64_t)threadIdx.x * kCompactPerThread + k;
+        if (kKind == 0) {
+            const float* a = reinterpret_cast<const float*>(src) + row * cols;
+            float* b = reinterpret_cast<float*>(dst) + (int64_t)rank * cols;
+            for (int c = 0; c < cols; ++c) b[c] = a[c];
+        } else {
+            const double* a = reinterpret_cast<const double*>(src) + row * cols;
+            double* b = reinterpret_cast<double*>(dst) + (int64_t)rank * cols;
+            for (int c = 0; c < cols; ++c) b[c] = a[c];
+        }
+        if (locations) {
+            int64_t idx[4], r = row;
+            for (int d = dims.n - 1; d >= 0; --d) { idx[d] = r % dims.size[d]; r /= dims.size[d]; }
+            int64_t* loc = locations + (int64_t)rank * dims.n;
+            for (int d = 1; d < dims.n; ++d) loc[d - 1] = idx[d];       // spatial indices ...
+            loc[dims.n - 1] = idx[0];                                   // ... then the batch index
+        }
+        ++rank;
+    }
+    (void)elem;
+}
+
+// dst rows = rows of `a` then rows of `b` (the torch.cat of sparse_ops.py:41), all float64 [*, cols]
+__global__ void __launch_bounds__(kBlock)
+concat_rows_kernel(const double* __restrict__ a, int64_t na, const double* __restrict__ b, int64_t nb, double* __restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += stride)
+        dst[i] = i < na ? a[i] : b[i - na];
+}
+
+// ---- online Temporal Active Focus: one bin of a batch of recordings, state carried on the device ----------
+// events f64 [N,5] (b, x, y, t, p) of one fetch step; the events with t_lo <= t < t_hi form the bin.  Per sample the
+// rule of generate_taf.py:19-58 applies (a sample without events in the bin is left untouched: no ageing).
+struct OnlineCell { uint32_t n; float s; };
+
+__global__ void __launch_bounds__(kBlock)
+taf_online_scatter_kernel(const double* __restrict__ ev, int64_t n, double t_lo, double t_hi, double t_span, int B, int H, int W,
+                          uint32_t* __restrict__ flags, OnlineCell* __restrict__ cells) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t HW = (int64_t)H * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double* r = ev + 5 * i;
+        const double t = r[3];
+        if (!(t >= t_lo) || !(t < t_hi)) continue;
+        const long long b = (long long)r[0], x = (long long)r[1], y = (long long)r[2], p = (long long)r[4];
+        if (b < 0 || b >= B || x < 0 || x >= W || y < 0 || y >= H || p < 0 || p > 1) continue;
+        OnlineCell* c = cells + 2 * (b * HW + y * W + x) + p;
+        atomicAdd(&c->n, 1u);
+        atomicAdd(&c->s, (float)((t - t_lo) / t_span) - 1.0f);      // driver :213-215, then taf_cuda's t - 1 (:25)
+        flags[b] = 1u;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+taf_online_update_kernel(uint32_t* __restrict__ flags, OnlineCell* __restrict__ cells, int B, int64_t HW,
+                         float* __restrict__ state, float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)B * HW; i += stride) {
+        const int64_t b = i / HW, pix = i - b * HW;
+        const bool any = flags[b] != 0u;
+        uint4 c = *reinterpret_cast<uint4*>(cells + 2 * i);         // {n0, s0, n1, s1}
+        if (c.x | c.z) *reinterpret_cast<uint4*>(cells + 2 * i) = make_uint4(0, 0, 0, 0);
+        const uint32_t nn[2] = {c.x, c.z};
+        const float ss[2] = {__uint_as_float(c.y), __uint_as_float(c.w)};
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            float v[K];
+            float* cell = state + (i * 2 + p) * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) v[k] = cell[k];
+            if (any) {
+                if (nn[p]) {
+                    const float mean = __fdiv_rn(ss[p], (float)nn[p] + 1e-8f);
+#pragma unroll
+                    for (int k = 0; k + 1 < K; ++k) v[k] = v[k + 1] - 1.0f;
+                    v[K - 1] = mean;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) v[k] -= 1.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) cell[k] = v[k];
+            }
+            if (out) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) out[((b * K + k) * 2 + p) * HW + pix] = v[k];     // [B, 2K, H, W], channel 2k + p
+            }
+        }
+    }
+}
+
+__global__ void clear_words_kernel(uint32_t* __restrict__ p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0u;
+}
+
 }  // namespace evrep
 
 using namespace evrep;
@@ -240,6 +442,88 @@ int evrep_event_queue_tensor(const float* events, int64_t n, int Q, int B, int H
         EVREP_LAUNCH_CHECK();
     }
     queue_emit_kernel<<<grid_for(cells * Q), kBlock, 0, st>>>(totals, cells, Q, out);
+    EVREP_LAUNCH_CHECK();
+    return EVREP_OK;
+}
+
+
+// Stable compaction front ends.  `block_scratch`: (n / 2048 + 2) u32.  The number of kept rows ends up in
+// block_scratch[n_blocks] on the device; the caller reads it back to size its views (torch.nonzero does the same).
+static int compact_blocks(int64_t n) { return (int)((n + kCompactRows - 1) / kCompactRows); }
+
+int64_t evrep_compact_scratch_bytes(int64_t n_rows) {
+    if (n_rows < 0) return EVREP_ERR_ARG;
+    return 4ll * (compact_blocks(n_rows) + 2);
+}
+
+int evrep_dense_to_sparse(const float* dense, const int64_t* sizes, int n_dims, int C, int64_t* locations, float* features,
+                          uint32_t* block_scratch, uint32_t** count_dev, evrep_stream_t stream) {
+    if (!dense || !sizes || n_dims < 1 || n_dims > 4 || C <= 0 || !locations || !features || !block_scratch) return EVREP_ERR_ARG;
+    CompactDims dims;
+    dims.n = n_dims;
+    int64_t n = 1;
+    for (int d = 0; d < 4; ++d) { dims.size[d] = d < n_dims ? sizes[d] : 1; if (d < n_dims) n *= sizes[d]; }
+    const int nb = compact_blocks(n);
+    cudaStream_t st = as_stream(stream);
+    if (count_dev) *count_dev = block_scratch + nb;
+    if (nb == 0) { clear_words_kernel<<<1, 32, 0, st>>>(block_scratch, 1); EVREP_LAUNCH_CHECK(); return EVREP_OK; }
+    compact_count_kernel<0><<<nb, kCompactBlock, 0, st>>>(dense, n, C, 0.0, block_scratch);
+    EVREP_LAUNCH_CHECK();
+    compact_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb);
+    EVREP_LAUNCH_CHECK();
+    compact_scatter_kernel<0><<<nb, kCompactBlock, 0, st>>>(dense, n, C, 0.0, block_scratch, features, locations, dims);
+    EVREP_LAUNCH_CHECK();
+    return EVREP_OK;
+}
+
+int evrep_event_memory_update(const double* memory, int64_t n_memory, const double* events, int64_t n_events, double keep_from,
+                              double* merged, double* memory_out, uint32_t* block_scratch, uint32_t** count_dev,
+                              evrep_stream_t stream) {
+    if (n_memory < 0 || n_events < 0 || !merged || !memory_out || !block_scratch) return EVREP_ERR_ARG;
+    if ((n_memory > 0 && !memory) || (n_events > 0 && !events)) return EVREP_ERR_ARG;
+    const int64_t n = n_memory + n_events;
+    const int nb = compact_blocks(n);
+    cudaStream_t st = as_stream(stream);
+    if (count_dev) *count_dev = block_scratch + nb;
+    if (nb == 0) { clear_words_kernel<<<1, 32, 0, st>>>(block_scratch, 1); EVREP_LAUNCH_CHECK(); return EVREP_OK; }
+    concat_rows_kernel<<<grid_for(5 * n), kBlock, 0, st>>>(memory, 5 * n_memory, events, 5 * n_events, merged);
+    EVREP_LAUNCH_CHECK();
+    compact_count_kernel<1><<<nb, kCompactBlock, 0, st>>>(merged, n, 5, keep_from, block_scratch);
+    EVREP_LAUNCH_CHECK();
+    compact_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb);
+    EVREP_LAUNCH_CHECK();
+    CompactDims dims; dims.n = 0; for (int d = 0; d < 4; ++d) dims.size[d] = 1;
+    compact_scatter_kernel<1><<<nb, kCompactBlock, 0, st>>>(merged, n, 5, keep_from, block_scratch, memory_out, nullptr, dims);
+    EVREP_LAUNCH_CHECK();
+    return EVREP_OK;
+}
+
+int64_t evrep_taf_online_scratch_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return EVREP_ERR_ARG;
+    return (int64_t)(B + 3) / 4 * 16 + (int64_t)B * H * W * 2 * (int64_t)sizeof(OnlineCell);
+}
+
+int evrep_taf_online_bin(const double* events, int64_t n, double t_lo, double t_hi, double t_span, int B, int H, int W, int K,
+                         float* state, float* out, void* scratch, evrep_stream_t stream) {
+    if (n < 0 || (n > 0 && !events) || B <= 0 || H <= 0 || W <= 0 || !state || !scratch || !(t_span > 0.0)) return EVREP_ERR_ARG;
+    cudaStream_t st = as_stream(stream);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(scratch);
+    OnlineCell* cells = reinterpret_cast<OnlineCell*>(reinterpret_cast<char*>(scratch) + (int64_t)(B + 3) / 4 * 16);
+    const int64_t HW = (int64_t)H * W;
+    if (n > 0) {
+        taf_online_scatter_kernel<<<grid_for(n), kBlock, 0, st>>>(events, n, t_lo, t_hi, t_span, B, H, W, flags, cells);
+        EVREP_LAUNCH_CHECK();
+    }
+    const int grid = grid_for((int64_t)B * HW);
+#define EVREP_ONLINE_K(KK) case KK: taf_online_update_kernel<KK><<<grid, kBlock, 0, st>>>(flags, cells, B, HW, state, out); break;
+    switch (K) {
+        EVREP_ONLINE_K(1) EVREP_ONLINE_K(2) EVREP_ONLINE_K(3) EVREP_ONLINE_K(4) EVREP_ONLINE_K(5) EVREP_ONLINE_K(6)
+        EVREP_ONLINE_K(7) EVREP_ONLINE_K(8) EVREP_ONLINE_K(9) EVREP_ONLINE_K(10) EVREP_ONLINE_K(11) EVREP_ONLINE_K(12)
+        default: return EVREP_ERR_ARG;
+    }
+#undef EVREP_ONLINE_K
+    EVREP_LAUNCH_CHECK();
+    clear_words_kernel<<<(B + 255) / 256, 256, 0, st>>>(flags, B);     // the cells were cleared by the update pass
     EVREP_LAUNCH_CHECK();
     return EVREP_OK;
 }

@@ -1,93 +1,148 @@
-"""Online (streaming) encoding -- drop-in for the reference's ``data/fetcher.py``.
+"""Online (streaming) encoding -- the role of the reference's ``data/fetcher.py`` (same three class
+names, constructor arguments, ``fetch()`` tuple, ``finish`` / ``iter`` / ``memory`` attributes), built
+for a device-resident stream:
 
-Same classes, constructor arguments and ``fetch()`` return tuple.  The reference keeps the
-batch's events in a host numpy array, selects the slice of every step with a boolean mask on
-the host and uploads it (``data/fetcher.py:35-50``); here the events are uploaded ONCE, sorted
-by time on the device, and every step is an index range found with two binary searches.
-``to_volume`` is one of the ``frlw_evd_b200.data.sparse_ops`` encoders (same plugin signature,
-``data/fetcher.py:53``).
+* the batch's events are uploaded ONCE and ordered by time on the device; the index range of every
+  step -- the reference selects it with a boolean mask over the whole host array and uploads the
+  selection, step after step (``data/fetcher.py:35-50``) -- comes from a table of cut points computed
+  for all steps by one ``searchsorted`` when the fetcher is built;
+* ``fetch()`` does not wait for the GPU: the encoder call is bracketed by CUDA events and
+  ``represent_time`` is read from them later (``represent_times()``); pass ``sync_timing=True`` for the
+  reference's blocking per-step number;
+* the labels are bucketed per batch sample once, so ``getLabels`` is two bisections per sample.
+
+``to_volume`` is any encoder with the plugin signature of ``frlw_evd_b200.data.sparse_ops``
+(``data/fetcher.py:53``), e.g. ``generate_taf_online_cuda``, whose FIFO state lives in ``memory`` on
+the device from step to step.
 """
 from __future__ import annotations
 
+import bisect
 import time
 
 import numpy as np
 import torch
 
+MAX_LABELS = 80          # data/fetcher.py:23
+WHOLE_RECORDING = 60000000   # data/fetcher.py:57: with a 60 s window the label time is the end of the recording
+
+
+class _TimeOrderedEvents:
+    """Rows ``(b, x, y, t, p)`` of a batch on the device, ordered by ``t`` (stable: rows with equal
+    timestamps keep the order a boolean mask over the original array would give them)."""
+
+    def __init__(self, events, device):
+        rows = torch.as_tensor(events).to(device)
+        order = torch.argsort(rows[..., 3], stable=True)
+        self.rows = rows[order].contiguous()
+        self.times = self.rows[..., 3].contiguous()
+
+    def cuts(self, edges):
+        """Index of the first row with ``t >= edge`` for every edge (one device call, one read back)."""
+        probe = torch.as_tensor(np.asarray(edges), dtype=self.times.dtype, device=self.times.device)
+        return torch.searchsorted(self.times, probe).cpu().tolist()
+
+
+class _LabelBuckets:
+    """Label rows ``(b, ..., t at column 6)`` grouped by batch sample and ordered by time."""
+
+    def __init__(self, labels, n_samples):
+        self.labels = labels
+        host = labels.detach().cpu().numpy()
+        self.rows, self.times = [], []
+        for b in range(n_samples):
+            idx = np.nonzero(host[:, 0] == b)[0]
+            idx = idx[np.argsort(host[idx, 6], kind="stable")]
+            self.rows.append(idx)
+            self.times.append(host[idx, 6])
+
+    def around(self, sample, when, tol):
+        """Rows of ``sample`` with ``|t - when| <= tol``, in the order of the label array."""
+        times = self.times[sample]
+        a, b = bisect.bisect_left(times, when - tol), bisect.bisect_right(times, when + tol)
+        return np.sort(self.rows[sample][a:b])
+
 
 class fetcher:
     def __init__(self, events, shape, labels, timestamps, filenames, events_window, event_volume_bins, infer_time, to_volume,
-                 device="cuda"):
-        self.events_window_abin = infer_time
-        self.events_window = events_window
-        self.event_volume_bins = event_volume_bins
-        self.shape = shape
-        self.memory = None
-        self.total_time = int(timestamps[0, 1] - timestamps[0, 0])
-        self.iter = 0
-        self.labels = labels
-        self.timestamps = timestamps
-        self.filenames = filenames
-        self.finish = False
+                 device="cuda", sync_timing=False):
+        self.shape, self.labels, self.timestamps, self.filenames = shape, labels, timestamps, filenames
+        self.events_window, self.events_window_abin, self.event_volume_bins = events_window, infer_time, event_volume_bins
         self.to_volume = to_volume
+        self.memory, self.iter, self.finish = None, 0, False
+        self.total_time = int(timestamps[0, 1] - timestamps[0, 0])
         self.device = torch.device(device)
-        ev = torch.as_tensor(events).to(self.device)
-        # a stable sort by time keeps the reference's event order inside every step (a boolean mask
-        # preserves the array order; steps are disjoint time ranges)
-        order = torch.argsort(ev[..., 3], stable=True)
-        self.events = ev[order].contiguous()
-        self._t = self.events[..., 3].contiguous()
+        self.sync_timing = sync_timing
+        self._stream = _TimeOrderedEvents(events, self.device)
+        self.events = self._stream.rows
+        self._buckets = None
+        # step k covers [clock[k], clock[k + 1]): the first one everything before `events_window`
+        self._clock = [None, events_window]
+        while self._clock[-1] < self.total_time:
+            self._clock.append(self._clock[-1] + infer_time)
+        self._cut = [0] + self._stream.cuts(self._clock[1:])
+        self._step = 0
+        self._events_pairs = []
 
-    def _range(self, lo, hi):
-        """Events with ``lo <= t < hi`` (``lo = None``: from the start)."""
-        t = self._t
-        a = 0 if lo is None else int(torch.searchsorted(t, torch.tensor([lo], dtype=t.dtype, device=t.device))[0])
-        b = int(torch.searchsorted(t, torch.tensor([hi], dtype=t.dtype, device=t.device))[0])
-        return self.events[a:b]
+    def _advance(self):
+        if self._step + 1 >= len(self._clock):           # fetch() past the end of the recording: extend the table
+            self._clock.append(self._clock[-1] + self.events_window_abin)
+            self._cut.append(self._stream.cuts([self._clock[-1]])[0])
+        lo, hi = self._cut[self._step], self._cut[self._step + 1]
+        self._step += 1
+        self.iter = self._clock[self._step]
+        self.finish = self.iter >= self.total_time
+        return self._stream.rows[lo:hi]
 
     def getLabels(self, timestamps):
-        max_labels = 80
+        """``data/fetcher.py:22-33``: per sample the labels within half a step of its timestamp, zero padded to
+        ``[B, 80, columns - 1]``; ``None`` as soon as one sample has none."""
+        if self._buckets is None:
+            self._buckets = _LabelBuckets(self.labels, len(self.timestamps))
         tol = self.events_window_abin / 2 - 1
-        padded_labels = torch.zeros((len(self.timestamps), max_labels, self.labels.shape[1] - 1)).float().to(self.labels.device)
-        for batch in range(len(self.timestamps)):
-            timestamp = timestamps[batch]
-            labels_ = self.labels[(self.labels[:, 0] == batch) & (self.labels[:, 6] + tol >= timestamp) &
-                                  (self.labels[:, 6] - tol <= timestamp)]
-            if len(labels_) == 0:
+        padded = torch.zeros((len(self.timestamps), MAX_LABELS, self.labels.shape[1] - 1), dtype=torch.float32,
+                             device=self.labels.device)
+        for sample in range(len(self.timestamps)):
+            rows = self._buckets.around(sample, float(timestamps[sample]), tol)
+            if len(rows) == 0:
                 return None
-            assert max_labels >= len(labels_)
-            padded_labels[batch, range(len(labels_))] = labels_[:, 1:].float()
-        return padded_labels
+            assert len(rows) <= MAX_LABELS
+            padded[sample, :len(rows)] = self.labels[torch.as_tensor(rows, device=self.labels.device)][:, 1:].float()
+        return padded
 
     def fetch(self):
-        if self.iter == 0:
-            events = self._range(None, self.events_window)                               # t < events_window
-            self.iter += self.events_window
-        else:
-            events = self._range(self.iter, self.iter + self.events_window_abin)         # iter <= t < iter + abin
-            self.iter += self.events_window_abin
-        if self.iter >= self.total_time:
-            self.finish = True
-        start = time.time()
+        events = self._advance()
+        on_gpu = self.device.type == "cuda"
+        tick = time.time()
+        if on_gpu and not self.sync_timing:
+            begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            begin.record()
         volume, self.memory = self.to_volume(events, len(self.timestamps), self.shape, self.iter, self.memory,
                                              self.events_window, self.event_volume_bins, self.events_window_abin)
-        if self.device.type == "cuda":
+        if on_gpu and not self.sync_timing:
+            end.record()
+            self._events_pairs.append((begin, end))
+        elif on_gpu:
             torch.cuda.synchronize()
-        represent_time = time.time() - start
-        if self.events_window == 60000000:
+        represent_time = time.time() - tick
+        if self.events_window == WHOLE_RECORDING:
             timestamps = self.timestamps[..., 1]
         else:
             timestamps = self.timestamps[..., 0] + self.iter
-        labels = self.getLabels(timestamps)
-        return volume, labels, timestamps, self.filenames, represent_time
+        return volume, self.getLabels(timestamps), timestamps, self.filenames, represent_time
+
+    def represent_times(self):
+        """Device time of every ``to_volume`` call so far in seconds (synchronises once)."""
+        if self._events_pairs:
+            self._events_pairs[-1][1].synchronize()
+        return [a.elapsed_time(b) * 1e-3 for a, b in self._events_pairs]
 
 
 class fetcherTrain(fetcher):
     def getLabels(self, timestamps):
+        """Training wants (class, box) instead of (box, class) (``data/fetcher.py:64-70``)."""
         labels = super().getLabels(timestamps)
-        if labels is not None:
-            return torch.cat([labels[:, :, 4:5], labels[:, :, :4]], dim=-1)
-        return None
+        return None if labels is None else torch.cat([labels[..., 4:5], labels[..., :4]], dim=-1)
 
 
 class fetcherVal(fetcher):

@@ -432,6 +432,29 @@ int evrep_sparse_event_frame(const double* events, int64_t n, int B, int H, int 
 int evrep_sparse_to_dense(const int64_t* locations, const float* features, int64_t n, int B, int H, int W, int C,
                           float* out, evrep_stream_t stream);
 
+/* S2 / S6 as device code, and an online TAF bin for the streaming driver (data/fetcher.py:35-62).
+ * evrep_dense_to_sparse: data/sparse_ops.py:123-135 -- rows of the dense tensor [sizes..., C] (1 to 4
+ *   leading dims, batch first) with a non-zero |.|-sum, in row-major order: locations int64 [N, n_dims]
+ *   (spatial indices, then the batch index) and features f32 [N, C].  Both outputs are sized for all
+ *   rows by the caller; N is left on the device at *count_dev (u32) -- read it back like
+ *   torch.nonzero does.  block_scratch: evrep_compact_scratch_bytes(rows) bytes.
+ * evrep_event_memory_update: :40-42 -- merged = cat(memory, events) (float64 [*,5]) and
+ *   memory_out = the rows of merged with column 3 >= keep_from, order kept; count at *count_dev.
+ * evrep_taf_online_bin: one 10 ms bin of a BATCH of recordings with the FIFO state carried on the
+ *   device: events float64 [N,5] (b, x, y, t, p) of a fetch step, of which t_lo <= t < t_hi form the
+ *   bin, t_norm = (t - t_lo) / t_span; per sample the rule of generate_taf.py:19-58 (a sample
+ *   without events in the bin is not aged).  state f32 [B,H,W,2,K] updated in place; out (nullable)
+ *   f32 [B,2K,H,W], channel 2k + p.  scratch: evrep_taf_online_scratch_bytes, zero on entry and return. */
+int64_t evrep_compact_scratch_bytes(int64_t n_rows);
+int evrep_dense_to_sparse(const float* dense, const int64_t* sizes, int n_dims, int C, int64_t* locations,
+                          float* features, uint32_t* block_scratch, uint32_t** count_dev, evrep_stream_t stream);
+int evrep_event_memory_update(const double* memory, int64_t n_memory, const double* events, int64_t n_events,
+                              double keep_from, double* merged, double* memory_out, uint32_t* block_scratch,
+                              uint32_t** count_dev, evrep_stream_t stream);
+int64_t evrep_taf_online_scratch_bytes(int B, int H, int W);
+int evrep_taf_online_bin(const double* events, int64_t n, double t_lo, double t_hi, double t_span, int B, int H,
+                         int W, int K, float* state, float* out, void* scratch, evrep_stream_t stream);
+
 /* -------------------- N1: data/event_representation_tool/src/event_queue_tensor.cpp:10-118 ----
  * As the extension behaves (its deques are never fed during the event loop): every event
  * (b, x, y, t, p, z) f32 [N,6] adds 1 - (start[b] + abin (z+1) - t) / abin to cell (p, b, y, x);
