@@ -16,7 +16,7 @@ import time
 import torch
 
 from . import ops
-from .recordings import DeviceRecording, Geometry, dump_u8, iter_recordings, parse_args
+from .recordings import DeviceRecording, Geometry, iter_recordings, parse_args
 
 
 def generate_eventframe(events, shape):
@@ -50,10 +50,10 @@ def encode_recording(rec: DeviceRecording, labels, geom: Geometry, sizes):
         yield label, list(u8)
 
 
-def encode_recording_stream(rec: DeviceRecording, labels, geom: Geometry, sizes, labels_per_call=128):
+def encode_chunks(rec: DeviceRecording, labels, geom: Geometry, sizes, labels_per_call=128):
     """Whole-recording form of ``encode_recording``: the nested last-N windows of ``labels_per_call``
     labels go through one bucketing + tile-kernel call (``ops.count_stream``) instead of
-    ``2 * len(sizes)`` launches per label.  Yields the same ``(label, [u8 [2,Ht,Wt] per N])``."""
+    ``2 * len(sizes)`` launches per label.  Yields ``(labels of the chunk, u8 [n_labels, len(sizes), 2, Ht, Wt])``."""
     ends = []
     for label in labels:
         end_count = rec.loader.seek_time(int(label))
@@ -66,32 +66,46 @@ def encode_recording_stream(rec: DeviceRecording, labels, geom: Geometry, sizes,
         local = [(lo - base, hi - base) for lo, hi in windows]
         try:
             frames = ops.count_stream(rec.events.slice(base, part[-1][1]), local, geom.grid, geom.coord_maps)
+            u8 = ops.count_lut_u8_batch(frames, geom.target, geom.resize_maps)
         except ops._lib.EvrepError as exc:
             if "out of range" not in str(exc):
                 raise
-            for label, _ in part:                  # windows span more segments than the ring holds: per-label path
-                yield from encode_recording(rec, [label], geom, sizes)
-            continue
-        u8 = ops.count_lut_u8_batch(frames, geom.target, geom.resize_maps)
-        for i, (label, _) in enumerate(part):
-            yield label, [u8[i * len(sizes) + k] for k in range(len(sizes))]
+            # windows span more segments than the ring holds: per-label path
+            u8 = torch.stack([torch.stack(list(frames)) for label, _ in part
+                              for _, frames in encode_recording(rec, [label], geom, sizes)])
+        yield [label for label, _ in part], u8.view(len(part), len(sizes), *u8.shape[-3:])
+
+
+def encode_recording_stream(rec: DeviceRecording, labels, geom: Geometry, sizes, labels_per_call=128):
+    """``encode_chunks`` label by label: yields the same ``(label, [u8 [2,Ht,Wt] per N])`` as ``encode_recording``."""
+    for chunk_labels, u8 in encode_chunks(rec, labels, geom, sizes, labels_per_call):
+        for i, label in enumerate(chunk_labels):
+            yield label, [u8[i, k] for k in range(len(sizes))]
 
 
 def main(argv=None):
+    from .recordings import AsyncWriter, PinnedRing
     args = parse_args("gen4", argv)
     geom = Geometry.for_dataset(args.dataset)
     sizes = windows_for(args.dataset)
+    writer, ring = AsyncWriter(), PinnedRing()
     total_time, total_count = 0.0, 0
     for mode, name, event_file, labels in iter_recordings(args.raw_dir, args.label_dir):
         rec = DeviceRecording(event_file)
         torch.cuda.synchronize()
-        tick = time.time()
-        for label, frames in encode_recording_stream(rec, labels, geom, sizes):
-            for n, u8 in zip(sizes, frames):
-                dump_u8(u8, args.target_dir, "EventCountImage{0}".format(n), mode, name + "_" + str(label) + ".npy")
-            total_count += 1
-        if mode == "test":
+        tick, count = time.time(), 0
+        for chunk_labels, u8 in encode_chunks(rec, labels, geom, sizes):
+            def emit(host, names=[name + "_" + str(label) + ".npy" for label in chunk_labels], mode=mode):
+                return [writer.put(host[i, k], args.target_dir, "EventCountImage{0}".format(n), mode, fname)
+                        for i, fname in enumerate(names) for k, n in enumerate(sizes)]
+            ring.push(u8, emit)          # device -> pinned ring -> files, behind the next chunk's kernels
+            count += len(chunk_labels)
+        if mode == "test":               # the reference times and counts the test split only (:97-99,161-163)
+            torch.cuda.synchronize()
             total_time += time.time() - tick
+            total_count += count
+    ring.flush()
+    writer.close()
     if total_count and total_time:
         print("Average Representation time: ", total_time / total_count)
 

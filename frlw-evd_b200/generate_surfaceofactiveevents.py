@@ -15,7 +15,7 @@ import time
 import torch
 
 from . import ops
-from .recordings import DeviceRecording, Geometry, dump_u8, iter_recordings, parse_args
+from .recordings import DeviceRecording, Geometry, iter_recordings, parse_args
 
 LAMDAS = [0.00001, 0.0000025, 0.000001]            # :103
 TIME_WINDOW = [554126, 2216505, 5541263]           # :104 (timed sub-windows, test mode)
@@ -92,14 +92,17 @@ def plan_windows(loader, labels):
     return plan
 
 
-def encode_recording_stream(rec: DeviceRecording, labels, geom: Geometry, labels_per_call=256):
-    """Whole-recording form of ``encode_recording``: one bucketing + tile-kernel call per
-    ``labels_per_call`` labels instead of two launches per label.  Yields the same
-    ``(label, u8 [L,2,Ht,Wt])``.  Falls back to the per-label path when the windows of
-    consecutive labels overlap (labels less than one window apart never do)."""
+def encode_chunks(rec: DeviceRecording, labels, geom: Geometry, labels_per_call=256):
+    """Whole-recording form of ``encode_recording``: one bucketing + tile-kernel call per ``labels_per_call``
+    labels instead of two launches per label.  Yields ``(labels of the chunk, u8 [n_labels, L, 2, Ht, Wt])``.
+    Falls back to the per-label path when the windows of consecutive labels overlap (labels less than one
+    window apart never do)."""
     plan = plan_windows(rec.loader, labels)
     if any(b[1] < a[2] for a, b in zip(plan, plan[1:])):
-        yield from encode_recording(rec, labels, geom)
+        per_label = list(encode_recording(rec, labels, geom))
+        for first in range(0, len(per_label), labels_per_call):
+            part = per_label[first:first + labels_per_call]
+            yield [label for label, _ in part], torch.stack([u8 for _, u8 in part])
         return
     time_of = rec.loader.time_of
     memory = None
@@ -107,26 +110,39 @@ def encode_recording_stream(rec: DeviceRecording, labels, geom: Geometry, labels
         part = plan[first:first + labels_per_call]
         windows = [(lo, hi, label, time_of(lo) if hi > lo else 0, time_of(hi - 1) if hi > lo else 0) for label, lo, hi in part]
         latest, memory = ops.sae_stream(rec.events, windows, geom.grid, memory, geom.coord_maps)
-        u8 = ops.sae_decay_u8_batch(latest, [w[2] for w in windows], LAMDAS, geom.target, geom.resize_maps)
-        for i, (label, _, _) in enumerate(part):
+        yield [label for label, _, _ in part], ops.sae_decay_u8_batch(latest, [w[2] for w in windows], LAMDAS, geom.target,
+                                                                      geom.resize_maps)
+
+
+def encode_recording_stream(rec: DeviceRecording, labels, geom: Geometry, labels_per_call=256):
+    """``encode_chunks`` label by label: yields the same ``(label, u8 [L,2,Ht,Wt])`` as ``encode_recording``."""
+    for chunk_labels, u8 in encode_chunks(rec, labels, geom, labels_per_call):
+        for i, label in enumerate(chunk_labels):
             yield label, u8[i]
 
 
 def main(argv=None):
+    from .recordings import AsyncWriter, PinnedRing
     args = parse_args("gen4", argv)
     geom = Geometry.for_dataset(args.dataset)
+    writer, ring = AsyncWriter(), PinnedRing()
     total_time, total_count = 0.0, 0
     for mode, name, event_file, labels in iter_recordings(args.raw_dir, args.label_dir):
         rec = DeviceRecording(event_file)
         torch.cuda.synchronize()
-        tick = time.time()
-        for label, u8 in encode_recording_stream(rec, labels, geom):
-            for j, lam in enumerate(LAMDAS):
-                dump_u8(u8[j], args.target_dir, "SurfaceOfActiveEvents{0}".format(lam), mode,
-                        name + "_" + str(label) + ".npy")
-            total_count += 1
-        if mode == "test":
+        tick, count = time.time(), 0
+        for chunk_labels, u8 in encode_chunks(rec, labels, geom):
+            def emit(host, names=[name + "_" + str(label) + ".npy" for label in chunk_labels], mode=mode):
+                return [writer.put(host[i, j], args.target_dir, "SurfaceOfActiveEvents{0}".format(lam), mode, fname)
+                        for i, fname in enumerate(names) for j, lam in enumerate(LAMDAS)]
+            ring.push(u8.contiguous(), emit)     # device -> pinned ring -> files, behind the next chunk's kernels
+            count += len(chunk_labels)
+        if mode == "test":               # the reference times and counts the test split only (:121-123,186-188)
+            torch.cuda.synchronize()
             total_time += time.time() - tick
+            total_count += count
+    ring.flush()
+    writer.close()
     if total_count and total_time:
         print("Average Representation time: ", total_time / total_count)
 

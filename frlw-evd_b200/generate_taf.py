@@ -136,19 +136,37 @@ class HostPipeline:
         self.fused_u8 = self.assume_ordered and tuple(geom.grid) == tuple(geom.target)
         self.vol = None if self.fused_u8 else torch.empty((max(max_w, 1), 2 * K, H, W), dtype=torch.float32, device=dev)
         self.violations = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ring = None                   # pinned chunk buffers of the `sink` mode, allocated on first use
         self.u8 = [torch.empty((max(max_w, 1), K, 2, Ht, Wt), dtype=torch.uint8, device=dev) for _ in range(2)]
         self.state = ops.taf_fresh_state(geom.grid, K, dev)
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.out_shape = (len(self.windows), K, 2, Ht, Wt)
 
-    def run(self, raw_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
-        """``raw_host``: pinned uint8 payload of the whole recording (8 bytes/event);
-        ``out_host``: pinned uint8 tensor of shape ``self.out_shape``."""
+    def run(self, raw_host: torch.Tensor, out_host: torch.Tensor = None, sink=None) -> torch.Tensor:
+        """``raw_host``: pinned uint8 payload of the whole recording (8 bytes/event).  The uint8 tensors go either
+        to ``out_host`` (pinned uint8 tensor of shape ``self.out_shape``) or, chunk by chunk, to
+        ``sink(first_window, last_window, host_array) -> futures``: then only a ring of three pinned chunk
+        buffers is page-locked, whatever the number of windows, and a buffer is reused once the futures its
+        ``sink`` call returned (the file writes) are done."""
+        assert (out_host is None) != (sink is None), "give either out_host or sink"
         ev = torch.cuda.Event
         in_done, raw_free, comp_done, out_done = ([ev() for _ in range(2)] for _ in range(4))
         start = torch.cuda.current_stream(self.device)
         for s in (self.s_in, self.s_comp, self.s_out):
             s.wait_stream(start)
+        if sink is not None and self.ring is None:
+            per = self.u8[0][0].numel()
+            self.ring = [dict(buf=torch.empty(self.u8[0].shape[0] * per, dtype=torch.uint8, pin_memory=True), done=None,
+                              span=None, futures=[]) for _ in range(3)]
+
+        def retire(slot):
+            if slot["span"] is not None:
+                slot["done"].synchronize()
+                a, b = slot["span"]
+                n = (b - a) * self.u8[0][0].numel()
+                slot["futures"] = list(sink(a, b, slot["buf"][:n].numpy().reshape((b - a,) + tuple(self.out_shape[1:]))) or [])
+                slot["span"] = None
+
         for c, (a, b) in enumerate(self.chunks):
             k = c & 1
             e0, e1 = self.windows[a][0], self.windows[b - 1][1]
@@ -180,12 +198,33 @@ class HostPipeline:
                 if self.assume_ordered:
                     self.violations += ops.order_violations_tensor(self.device)
                 comp_done[k].record(self.s_comp)
+            if sink is not None:
+                if c:
+                    retire(self.ring[(c - 1) % 3])           # the previous chunk has had a whole chunk of kernels to land
+                slot = self.ring[c % 3]
+                retire(slot)
+                for f in slot["futures"]:
+                    f.result()                               # its files are written: the buffer is free
+                slot["futures"] = []
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(comp_done[k])
-                out_host[a:b].copy_(self.u8[k][:b - a], non_blocking=True)
+                if sink is None:
+                    out_host[a:b].copy_(self.u8[k][:b - a], non_blocking=True)
+                else:
+                    slot["buf"][:(b - a) * self.u8[0][0].numel()].copy_(self.u8[k][:b - a].reshape(-1), non_blocking=True)
                 out_done[k].record(self.s_out)
+                if sink is not None:
+                    slot["done"], slot["span"] = ev(), (a, b)
+                    slot["done"].record(self.s_out)
         for s in (self.s_in, self.s_comp, self.s_out):
             start.wait_stream(s)
+        if sink is not None:
+            for slot in self.ring:
+                retire(slot)
+            for slot in self.ring:
+                for f in slot["futures"]:
+                    f.result()
+                slot["futures"] = []
         return out_host
 
     def order_violations(self) -> int:
@@ -198,21 +237,22 @@ class HostPipeline:
 def encode_recording_to_files(rec: DeviceRecording, labels, name: str, mode: str, target_dir: str, geom: Geometry,
                               writer, volume_bins=VOLUME_BINS, abin=ABIN) -> int:
     """Host pipeline + file layout of ``generate_taf.py:226-235``: pinned ``.dat`` payload in,
-    ``taf/<mode>/bins{K/2}`` and ``bins{K}`` files out.  Returns the number of windows."""
+    ``taf/<mode>/bins{K/2}`` and ``bins{K}`` files out, chunk by chunk through a ring of three pinned
+    buffers (the page-locked memory does not grow with the number of labels).  Returns the number of windows."""
     plan = plan_windows(rec.loader, labels, abin, volume_bins)
     if not plan:
         return 0
     pipe = HostPipeline(geom, plan, volume_bins, abin)
-    out = torch.empty(pipe.out_shape, dtype=torch.uint8, pin_memory=True)
-    pipe.run(rec.raw_pinned, out)
-    torch.cuda.synchronize()
     half = volume_bins // 2
-    host = out.numpy()
-    for i, w in enumerate(plan):
-        fname = name + "_" + str(w.label) + ".npy"
-        writer.put(host[i, :half], target_dir, "taf", mode, "bins{0}".format(half), fname)
-        writer.put(host[i, half:], target_dir, "taf", mode, "bins{0}".format(volume_bins), fname)
-    writer.drain()                       # `out` is released when this returns
+
+    def sink(a, b, host):
+        futures = []
+        for i, w in enumerate(plan[a:b]):
+            fname = name + "_" + str(w.label) + ".npy"
+            futures.append(writer.put(host[i, :half], target_dir, "taf", mode, "bins{0}".format(half), fname))
+            futures.append(writer.put(host[i, half:], target_dir, "taf", mode, "bins{0}".format(volume_bins), fname))
+        return futures
+    pipe.run(rec.raw_pinned, sink=sink)
     return len(plan)
 
 
