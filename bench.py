@@ -136,6 +136,112 @@ def cpu_reference_leg(t, x, y, p, windows, sample_windows, repeats=1):
     return n_ev / best / 1e6, n_ev, best, threads
 
 
+def cpu_reference_driver_leg(t, x, y, p, windows, sample_windows):
+    """the reference DRIVER end to end on the host -- .dat file on disk, loader decode,
+    float64 staging, the encode loops, leaky transform, flip, uint8, file writes (`generate_taf.py:78-243`, oracle
+    port `oracle.drivers.run_taf`) -- for the first `sample_windows` labels.  Returns (Mevents/s, events, seconds)."""
+    import tempfile
+    import torch
+    from frlw_evd_b200 import synth
+    from oracle import drivers as od
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = windows[:sample_windows]
+    hi = sample[-1][1]
+    n_ev = sum(w[1] - w[0] for w in sample)
+    labels = synth.label_times(int(t[hi - 1]) + 2)[:sample_windows]
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "raw", "test"))
+        synth.write_dat(os.path.join(tmp, "raw", "test", "rec_td.dat"), t[:hi + 1], x[:hi + 1], y[:hi + 1], p[:hi + 1], *SENSOR)
+        synth.write_bbox_npy(os.path.join(tmp, "raw", "test", "rec_bbox.npy"), labels)
+        tick = time.perf_counter()
+        od.run_taf(os.path.join(tmp, "raw"), os.path.join(tmp, "raw"), os.path.join(tmp, "out"), "gen4")
+        dt = time.perf_counter() - tick
+    return n_ev / dt / 1e6, n_ev, dt
+
+
+def parity_check(ev, windows, t, x, y, p, maps, n_check=3):
+    """Outside every timed region: the first windows of the benchmark's own workload (a fresh 10-bin window and two
+    incremental 5-bin ones) through the kernels that are timed, against the CPU oracle.  The oracle is the checker only."""
+    import torch
+    from frlw_evd_b200 import ops
+    from oracle import drivers as od
+    sample = windows[:n_check]
+    hi = sample[-1][1]
+    staged = torch.from_numpy(np.stack([x[:hi], y[:hi], t[:hi], p[:hi]], 1).astype(np.float64))
+    want, want_state = od.taf_windows_in_memory(staged, sample, ABIN, GRID, K, scale=(GRID[1] / SENSOR[1], GRID[0] / SENSOR[0]))
+    state = ops.taf_fresh_state(GRID, K, ev.device)
+    got = ops.taf_stream(ev, sample, ABIN, GRID, K, state, maps).cpu()
+    worst = 0.0
+    ok = True
+    for i in range(n_check):
+        a, b = got[i].numpy(), want[i].numpy()
+        ok = ok and bool(np.allclose(a, b, rtol=1e-5, atol=1e-6))
+        worst = max(worst, float(np.max(np.abs(a - b) / (1e-6 + 1e-5 * np.abs(b)))))
+    ok = ok and bool(np.allclose(state.cpu().numpy(), want_state.numpy(), rtol=1e-5, atol=1e-6))
+    return {"ok": ok, "windows": n_check, "events": int(sum(w[1] - w[0] for w in sample)), "tolerance": "1e-5 rel + 1e-6 abs",
+            "worst_error_over_tolerance": worst, "against": "oracle.drivers.taf_windows_in_memory (CPU, float32 like the reference)"}
+
+
+def ev_record(ev, t, seconds, maps, out, peak, steps, barrier):
+    """The second north-star encoder on the same stream: Event Volume K=8, 50 ms windows back to back, through the span
+    kernels (slice sort + tile kernel); device-resident, CUDA-event timed."""
+    import bisect
+    import torch
+    from frlw_evd_b200 import ops
+    edges = list(range(0, int(seconds * 1e6) + 1, 50000))
+    wins = [(bisect.bisect_left(t, a), bisect.bisect_left(t, b), a, 50000) for a, b in zip(edges[:-1], edges[1:])]
+    segments, spans = ops.plan_ev_spans(wins, lambda i: int(t[i]), lambda T, lo, hi: bisect.bisect_left(t, T, lo, hi))
+    n_ev = sum(w[1] - w[0] for w in wins)
+    need = len(wins) * 2 * K * GRID[0] * GRID[1]
+    vol = (out.view(-1)[:need] if out.numel() >= need else torch.empty(need, dtype=torch.float32, device=ev.device)).view(len(wins), 2 * K, *GRID)
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for _ in range(3):
+        ops.event_volume_spans(ev, segments, spans, GRID, K, maps, vol)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record()
+    for i in range(steps):
+        ops.event_volume_spans(ev, segments, spans, GRID, K, maps, vol, tile_events=pairs[i])
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b) / steps
+    tile_ms = statistics.mean(x.elapsed_time(y) for x, y in pairs)
+    algo = 9 * n_ev + len(wins) * 4 * 2 * K * GRID[0] * GRID[1]
+    return {"metric": "Mevents/s encoded (Event Volume K=8, 1MP)", "value": n_ev / (ms * 1e-3) / 1e6, "unit": "Mevents/s",
+            "ms_per_step": ms, "windows": len(wins), "events": n_ev, "kernel": "ev_slice_tile_kernel", "kernel_ms": tile_ms,
+            "algorithmic_bytes_per_launch": algo, "frac": algo / (tile_ms * 1e-3) / 1e9 / peak,
+            "step_frac": algo / (ms * 1e-3) / 1e9 / peak,
+            "path": "evrep_event_volume_spans: bins by bisection + slice sort + tile kernel (float32 [2K,H,W] per window)"}
+
+
+def copy_floor(raw_host, u8_host, dev, barrier, reps=3):
+    """The same bytes as one e2e step, nothing but the copies: pinned -> device and device -> pinned at the same time
+    on two streams, every rank at once.  The e2e step cannot be faster than this."""
+    import torch
+    d_in = torch.empty(raw_host.numel(), dtype=torch.uint8, device=dev)
+    d_out = torch.empty(u8_host.numel(), dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    flat_out = u8_host.view(-1)
+
+    def once():
+        cur = torch.cuda.current_stream(dev)
+        s1.wait_stream(cur); s2.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            d_in.copy_(raw_host, non_blocking=True)
+        with torch.cuda.stream(s2):
+            flat_out.copy_(d_out, non_blocking=True)
+        cur.wait_stream(s1); cur.wait_stream(s2)
+    once()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record()
+    for _ in range(reps):
+        once()
+    b.record()
+    barrier()
+    return a.elapsed_time(b) / reps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,13 +278,19 @@ def main():
         total = time.perf_counter() - tick
         value = statistics.mean(vals)
         sample = "first %d windows (%d events) of the workload per step, encoder loops of generate_taf.py:195-222" % (args.cpu_windows, n_ev)
+        # the driver end to end (file decode, float64 staging, encode, leaky, uint8, file writes)
+        drv_windows = max(2, min(args.cpu_windows, 24))
+        drv_value, drv_events, drv_seconds = cpu_reference_driver_leg(t, x, y, p, windows, drv_windows)
         print(json.dumps({
             "impl": "reference", "metric": "Mevents/s encoded (TAF K=8, 1MP)", "value": value, "unit": "Mevents/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
             "cpu_baseline": {"value": value, "unit": "Mevents/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e": {"value": drv_value, "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "what": "the reference driver end to end on the host (BASELINE.md section 3 ii): .dat file -> loader decode -> "
+                            "float64 staging -> encode loops -> leaky / flip / uint8 -> files; first %d labels (%d events), "
+                            "%.1f s" % (drv_windows, drv_events, drv_seconds)},
         }))
         return
 
@@ -218,6 +330,8 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    check = parity_check(ev, windows, t, x, y, p, maps) if rank == 0 else None
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -266,6 +380,8 @@ def main():
         with open(traffic_file) as fh:
             roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
 
+    ev_rec = ev_record(ev, t, args.seconds, maps, out, peak, max(2, min(args.steps, 10)), barrier)
+
     # end to end through the public call with host buffers
     e2e = None
     if not args.no_e2e:
@@ -295,7 +411,13 @@ def main():
             tmax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             e2e_ms = float(tmax[0])
+        floor_ms = copy_floor(raw_host, u8_host, dev, barrier)
+        if world > 1:
+            tmax = torch.tensor([floor_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            floor_ms = float(tmax[0])
         e2e = {"value": total_events / (e2e_ms * 1e-3) / 1e6, "unit": "Mevents/s", "ms_per_step": e2e_ms,
+               "copy_floor_ms": floor_ms, "copy_floor_note": "the step's bytes, both directions at once, all ranks at once, no kernels",
                "h2d_bytes_per_step": int(raw_host.numel()), "d2h_bytes_per_step": int(u8_host.numel()),
                "path": "pinned .dat bytes -> H2D -> decode -> taf_stream -> leaky uint8 [K,2,Ht,Wt] -> D2H, "
                        "12-window chunks on three streams (generate_taf.HostPipeline)"}
@@ -325,6 +447,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu,
             "windows": nw, "events_in_windows_per_gpu": n_in_windows, "host_placement": placement,
+            "parity_check": check, "ev": ev_rec,
         }))
     if world > 1:
         dist.destroy_process_group()
