@@ -1,3 +1,5 @@
+#include <algorithm>
+
 #include "stream_common.cuh"
 
 namespace evrep {
@@ -15,8 +17,9 @@ namespace evrep {
 // Saturation is harmless: the image value depends on min(count, 20) only (:32-34), and
 // min(sum of min(n_g, 255), 255) >= 20 exactly when the true sum is.  The value LUT, the nearest
 // resize and the uint8 output are one batched pass over the frames (evrep_count_lut_u8_batch).
-constexpr int kCountThreads = 512;
-constexpr int kCountTilesPerSm = 2;
+constexpr int kCountThreads = 128;       // a segment brings a tile tens to hundreds of records: small CTAs, many of them
+constexpr int kCountTilesPerSm = 2;      // tile size of the bucketing layout (tiles = 2 x SMs)
+constexpr int kCountCtasPerSm = 8;       // resident CTAs the kernel is compiled for: groups of segments run side by side
 constexpr int kCountMaxSmem = 112 * 1024;
 
 struct CountSegment {        // per segment: the emissions that follow it
@@ -33,9 +36,13 @@ struct CountTileParams {
     uint8_t* frames;         // u8 [n_emits][2,H,W]
     int64_t frame_stride;
     int depth;               // ring slots
+    int seg_per_group;       // blockIdx.y = group: it emits the windows that end in its segments [y * spg, (y + 1) * spg)
 };
 
-__global__ void __launch_bounds__(kCountThreads, kCountTilesPerSm)
+// Windows of different labels are independent, so the segment axis is cut into groups that run as separate CTAs
+// (blockIdx.y): a group first counts the depth - 1 segments before its own (their slots feed its first windows,
+// nothing is emitted for them), then walks its own segments.
+__global__ void __launch_bounds__(kCountThreads, kCountCtasPerSm)
 count_tile_kernel(CountTileParams tp) {
     const StreamPlan& pl = tp.pl;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -54,13 +61,22 @@ count_tile_kernel(CountTileParams tp) {
     const uint32_t* my_records = pl.records + pl.tile_base[tile];
     const uint32_t list_len = (pl.tile_total[tile] + 3u) & ~3u;
     const int n_chunks = (int)((list_len + kWsChunkRecords - 1) / kWsChunkRecords);
-    auto issue = [&](int c) {           // thread 0 only
-        const uint32_t first = (uint32_t)c * kWsChunkRecords;
+    const int TB = pl.TB;
+    const int g_begin = (int)blockIdx.y * tp.seg_per_group;                               // first segment this CTA emits for
+    const int g_end = min(TB, g_begin + tp.seg_per_group);
+    const int g_walk = max(0, g_begin - (tp.depth - 1));                                   // first segment it counts
+    if (g_begin >= TB) return;
+    // the ring is indexed relative to the chunk that holds the first record of segment g_walk
+    const int chunk0 = (int)(__ldg(my_off + g_walk) / kWsChunkRecords);
+    const uint32_t rec0 = (uint32_t)chunk0 * kWsChunkRecords;
+    auto issue = [&](int c) {           // thread 0 only; c counts from chunk0
+        const uint32_t first = (uint32_t)(chunk0 + c) * kWsChunkRecords;
         const uint32_t bytes = min((uint32_t)kWsChunkRecords, list_len - first) * 4u;
         uint64_t* bar = full + (c % kWsStages);
         mbar_expect_tx(bar, bytes);
         tma_load_1d(ring + (c % kWsStages) * kWsChunkRecords, my_records + first, bytes, bar);
     };
+    const int n_rel = n_chunks - chunk0;                                                   // chunks from chunk0 to the end of the list
     if (tid == 0) {
         for (int s = 0; s < kWsStages; ++s) mbar_init(full + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -68,30 +84,29 @@ count_tile_kernel(CountTileParams tp) {
     for (uint32_t i = tid; i < 2 * P; i += kCountThreads) acc[i] = 0u;
     __syncthreads();
     if (tid == 0)
-        for (int c = 0; c < n_chunks && c < kWsStages; ++c) issue(c);
+        for (int c = 0; c < n_rel && c < kWsStages; ++c) issue(c);
 
     // record range and emission list of segment g: lane l of every warp holds those of segment
     // group*32 + l, the next group of 32 is loaded one group ahead
-    const int TB = pl.TB;
     auto load_group = [&](int first, uint32_t& lo, uint32_t& hi, CountSegment& info) {
         const int g = min(first + lane, TB - 1);
-        lo = __ldg(my_off + g); hi = __ldg(my_off + g + 1);
+        lo = __ldg(my_off + g) - rec0; hi = __ldg(my_off + g + 1) - rec0;      // record positions relative to chunk0
         info = tp.segments[g];
     };
     uint32_t b_lo, b_hi, nb_lo = 0, nb_hi = 0;
     CountSegment b_info, nb_info = {};
-    load_group(0, b_lo, b_hi, b_info);
+    load_group(g_walk, b_lo, b_hi, b_info);
 
     int ready_chunk = -1, next_refill = kWsStages;
-    for (int g = 0; g < TB; ++g) {
-        if ((g & 31) == 0) {
-            if (g) { b_lo = nb_lo; b_hi = nb_hi; b_info = nb_info; }
-            if (g + 32 < TB) load_group(g + 32, nb_lo, nb_hi, nb_info);
+    for (int g = g_walk; g < g_end; ++g) {
+        const int src = (g - g_walk) & 31;
+        if (src == 0) {
+            if (g != g_walk) { b_lo = nb_lo; b_hi = nb_hi; b_info = nb_info; }
+            if (g + 32 < g_end) load_group(g + 32, nb_lo, nb_hi, nb_info);
         }
-        const int src = g & 31;
         const uint32_t o0 = __shfl_sync(0xFFFFFFFFu, b_lo, src), o1 = __shfl_sync(0xFFFFFFFFu, b_hi, src);
         const int emit_first = __shfl_sync(0xFFFFFFFFu, b_info.emit_first, src);
-        const int emit_count = __shfl_sync(0xFFFFFFFFu, b_info.emit_count, src);
+        const int emit_count = g >= g_begin ? __shfl_sync(0xFFFFFFFFu, b_info.emit_count, src) : 0;
         uint32_t cur = o0;
         while (cur < o1) {
             const uint32_t avail = (uint32_t)next_refill * kWsChunkRecords;     // records requested so far
@@ -110,7 +125,7 @@ count_tile_kernel(CountTileParams tp) {
                 __syncthreads();
                 const int drained = (int)(cur / kWsChunkRecords);
                 if (tid == 0)
-                    for (int r = next_refill; r < drained + kWsStages && r < n_chunks; ++r) issue(r);
+                    for (int r = next_refill; r < drained + kWsStages && r < n_rel; ++r) issue(r);
                 next_refill = drained + kWsStages;
             }
         }
@@ -119,7 +134,7 @@ count_tile_kernel(CountTileParams tp) {
             const int drained = (int)(o1 / kWsChunkRecords);
             if (drained + kWsStages > next_refill) {
                 if (tid == 0)
-                    for (int r = next_refill; r < drained + kWsStages && r < n_chunks; ++r) issue(r);
+                    for (int r = next_refill; r < drained + kWsStages && r < n_rel; ++r) issue(r);
                 next_refill = drained + kWsStages;
             }
         }
@@ -216,8 +231,16 @@ int evrep_count_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, 
     tp.pl = pl; tp.segments = reinterpret_cast<const CountSegment*>(extra);
     tp.emits = reinterpret_cast<const CountEmit*>(extra + seg_bytes);
     tp.frames = frames_out; tp.frame_stride = frame_stride; tp.depth = depth;
+    // groups of segments: enough CTAs for two rounds of what the SMs hold at once, each group long enough that the
+    // depth - 1 segments it counts again for its first windows stay a small part of its work
+    const int per_sm = (int)std::min<size_t>((size_t)kCountCtasPerSm, (size_t)(224 * 1024) / (smem + 1024));
+    const int want_groups = std::max(1, 2 * per_sm * sm_count() / std::max(1, L.n_tiles));
+    const int min_len = std::max(8, 4 * depth);
+    int groups = std::max(1, std::min(want_groups, n_segments / min_len));
+    tp.seg_per_group = (n_segments + groups - 1) / groups;
+    groups = (n_segments + tp.seg_per_group - 1) / tp.seg_per_group;
     EVREP_CUDA(cudaFuncSetAttribute(count_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    count_tile_kernel<<<L.n_tiles, kCountThreads, smem, st>>>(tp);
+    count_tile_kernel<<<dim3((unsigned)L.n_tiles, (unsigned)groups), kCountThreads, smem, st>>>(tp);
     EVREP_LAUNCH_CHECK();
     return EVREP_OK;
 }

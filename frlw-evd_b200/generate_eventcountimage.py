@@ -54,11 +54,8 @@ def encode_chunks(rec: DeviceRecording, labels, geom: Geometry, sizes, labels_pe
     """Whole-recording form of ``encode_recording``: the nested last-N windows of ``labels_per_call``
     labels go through one bucketing + tile-kernel call (``ops.count_stream``) instead of
     ``2 * len(sizes)`` launches per label.  Yields ``(labels of the chunk, u8 [n_labels, len(sizes), 2, Ht, Wt])``."""
-    ends = []
-    for label in labels:
-        end_count = rec.loader.seek_time(int(label))
-        if end_count is not None:
-            ends.append((label, int(end_count)))
+    found = rec.loader.seek_index_many(labels)                # seek_time of every label at once
+    ends = [(label, int(end)) for label, end in zip(labels, found) if end >= 0]
     for first in range(0, len(ends), labels_per_call):
         part = ends[first:first + labels_per_call]
         windows = [(max(end - n, 0), end) for _, end in part for n in sizes]          # events[-N:] (:156)

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import time
 
+import numpy as np
 import torch
 
 from . import ops
@@ -72,24 +73,23 @@ def encode_recording(rec: DeviceRecording, labels, geom: Geometry, mode="train")
 def plan_windows(loader, labels):
     """The driver's window of every label (:147-175) as ``(label, ev_begin, ev_end)``; in test
     mode the reference also encodes two shorter sub-windows first, which only time the encoder:
-    they are subsets of the largest one and leave the same state behind."""
-    plan = []
-    t_upper, c_upper = -100000000, 0
-    for label in labels:
-        end_time = int(label)
-        end_count = loader.seek_time(end_time)
-        if end_count is None:
-            continue
-        start_time = end_time - EVENTS_WINDOW
-        start_count = loader.seek_time(0 if start_time < 0 else start_time)
-        if start_count is None or start_time < 0:
-            start_count = 0
-        if start_time <= t_upper:
-            start_count = c_upper
-        t_upper, c_upper = label, end_count
-        lo = loader.upper_index(end_time - max(TIME_WINDOW), start_count, end_count)
-        plan.append((label, int(lo), int(end_count)))
-    return plan
+    they are subsets of the largest one and leave the same state behind.  All labels at once
+    (numpy): the per-label ``seek_time`` calls of the reference are index look-ups here."""
+    labels = np.asarray(labels, dtype=np.int64)
+    end_count = loader.seek_index_many(labels)
+    keep = end_count >= 0                                    # `if end_count is None: continue`
+    labels, end_count = labels[keep], end_count[keep]
+    if labels.size == 0:
+        return []
+    start_time = labels - EVENTS_WINDOW
+    start_count = loader.seek_index_many(np.where(start_time < 0, 0, start_time))
+    start_count = np.where((start_count < 0) | (start_time < 0), 0, start_count)
+    # a window that would reach back before the previous label starts where that one ended (:165-167)
+    prev_label = np.concatenate([[-100000000], labels[:-1]])
+    prev_end = np.concatenate([[0], end_count[:-1]])
+    start_count = np.where(start_time <= prev_label, prev_end, start_count)
+    lo = loader.upper_index_many(labels - max(TIME_WINDOW), start_count, np.maximum(end_count, start_count))
+    return [(labels[i], int(lo[i]), int(end_count[i])) for i in range(labels.size)]
 
 
 def encode_chunks(rec: DeviceRecording, labels, geom: Geometry, labels_per_call=256):

@@ -133,6 +133,52 @@ class PSEELoader(object):
         self.done = self._pos >= self._ev_count
         return lo, hi
 
+    # -- the same queries for many timestamps at once (numpy; the cursor does not move) ----------------
+    def _bisect_many(self, keys, lo, hi, right):
+        """Vectorised ``bisect_left`` / ``bisect_right`` of ``keys`` inside the index ranges ``[lo, hi)``."""
+        keys = np.asarray(keys, dtype=np.int64)
+        lo = np.broadcast_to(np.asarray(lo, dtype=np.int64), keys.shape).copy()
+        hi = np.broadcast_to(np.asarray(hi, dtype=np.int64), keys.shape).copy()
+        open_ = lo < hi
+        while open_.any():
+            mid = (lo + hi) >> 1
+            probe = self._t[np.where(open_, mid, 0)].astype(np.int64)
+            go_right = (probe <= keys) if right else (probe < keys)
+            lo = np.where(open_ & go_right, mid + 1, lo)
+            hi = np.where(open_ & ~go_right, mid, hi)
+            open_ = lo < hi
+        return lo
+
+    def lower_index_many(self, times, lo, hi):
+        return self._bisect_many(times, lo, hi, right=False)
+
+    def upper_index_many(self, times, lo, hi):
+        return self._bisect_many(times, lo, hi, right=True)
+
+    def seek_index_many(self, times, term_criterion=100000):
+        """What ``seek_time`` returns for every entry of ``times`` (``-1`` where it returns ``None``), including
+        its coarse phase that stops at the first probe that hits the timestamp exactly (:204-217), which on files
+        with repeated timestamps need not be the leftmost one."""
+        times = np.asarray(times, dtype=np.int64)
+        out = np.full(times.shape, -1, dtype=np.int64)
+        live = (times <= self.total_time()) & (times > 0) if self._ev_count else np.zeros(times.shape, dtype=bool)
+        lo = np.zeros(times.shape, dtype=np.int64)
+        hi = np.full(times.shape, self._ev_count, dtype=np.int64)
+        coarse = live & (hi - lo > term_criterion)
+        while coarse.any():
+            mid = (lo + hi) >> 1
+            probe = self._t[np.where(coarse, mid, 0)].astype(np.int64)
+            above, below = coarse & (probe > times), coarse & (probe < times)
+            hit = coarse & ~above & ~below
+            out[hit] = mid[hit]
+            live &= ~hit
+            hi = np.where(above, mid, hi)
+            lo = np.where(below, mid + 1, lo)
+            coarse = live & (hi - lo > term_criterion)
+        fine = self._bisect_many(times, np.where(live, lo, 0), np.where(live, hi, 0), right=False)
+        out[live] = fine[live]
+        return out
+
     def lower_index(self, time_us, lo, hi):
         """First index in ``[lo, hi)`` whose timestamp is ``>= time_us``."""
         return bisect.bisect_left(self._t, time_us, lo, hi)

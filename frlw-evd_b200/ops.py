@@ -28,6 +28,20 @@ def _stream(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _records(rows, struct):
+    """A list of tuples as a packed array of the ctypes ``struct`` (one numpy conversion instead of a Python object
+    per row).  Returns ``(keep-alive array, c_void_p)``."""
+    dtype = np.dtype([(name, np.dtype(ctype)) for name, ctype in struct._fields_], align=False)
+    assert dtype.itemsize == ctypes.sizeof(struct), struct
+    n = len(rows)
+    arr = np.zeros(max(n, 1), dtype=dtype)
+    if n:
+        cols = np.asarray(rows, dtype=np.int64).reshape(n, len(struct._fields_))
+        for k, (name, _) in enumerate(struct._fields_):
+            arr[name][:n] = cols[:, k]
+    return arr, ctypes.c_void_p(arr.ctypes.data)
+
+
 def _need_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -339,11 +353,8 @@ def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=N
     _need_cuda(ev.t, state)
     H, W = shape
     nw = len(windows)
-    arr = (_lib.TafWindow * nw)()
-    total_bins = 0
-    for i, w in enumerate(windows):
-        arr[i] = _lib.TafWindow(int(w[0]), int(w[1]), int(w[2]), int(w[3]), int(w[4]))
-        total_bins += int(w[3])
+    keep, arr = _records([tuple(w[:5]) for w in windows], _lib.TafWindow)
+    total_bins = sum(int(w[3]) for w in windows)
     if out is None and want_f32:
         out = torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=ev.device)
     assert state.is_contiguous() and (out is None or out.is_contiguous())
@@ -359,7 +370,7 @@ def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=N
         if out_u8 is not None:
             assert out_u8.is_contiguous() and out_u8.dtype == torch.uint8 and out_u8.numel() >= nw * 2 * K * H * W
         _lib.call("evrep_taf_stream_ordered", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
-                  ctypes.cast(arr, ctypes.c_void_p), nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
+                  arr, nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
                   int(bool(emit_state_every_window)), _ptr(out), 2 * K * H * W, _ptr(out_u8), 2 * K * H * W,
                   _ptr(buf), buf.numel(),
                   _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
@@ -370,7 +381,7 @@ def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=N
     buf = workspace("taf_stream", need, ev.device)
     vol = out if out is not None else torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=ev.device)
     _lib.call("evrep_taf_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
-              ctypes.cast(arr, ctypes.c_void_p), nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
+              arr, nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
               int(bool(emit_state_every_window)), _ptr(vol), 2 * K * H * W, _ptr(buf), buf.numel(),
               _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
     if out_u8 is not None:
@@ -470,9 +481,7 @@ def event_volume_stream(ev: EventStream, windows, tw: int, shape, K: int, maps=N
     _need_cuda(ev.t)
     H, W = shape
     nw = len(windows)
-    arr = (_lib.EvWindow * nw)()
-    for i, w in enumerate(windows):
-        arr[i] = _lib.EvWindow(int(w[0]), int(w[1]), int(w[2]))
+    keep, arr = _records([tuple(w[:3]) for w in windows], _lib.EvWindow)
     if out is None:
         out = torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=ev.device)
     assert out.is_contiguous()
@@ -482,7 +491,7 @@ def event_volume_stream(ev: EventStream, windows, tw: int, shape, K: int, maps=N
     buf = workspace("taf_stream", need, ev.device)
     xm, ym = _maps(maps)
     _lib.call("evrep_event_volume_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
-              ctypes.cast(arr, ctypes.c_void_p), nw, int(tw), H, W, K, xm, ym,
+              arr, nw, int(tw), H, W, K, xm, ym,
               maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W,
               _ptr(out), 2 * K * H * W, _ptr(buf), buf.numel(), _stream(ev.device))
     return out
@@ -539,12 +548,8 @@ def event_volume_spans(ev: EventStream, segments, spans, shape, K: int, maps=Non
     _need_cuda(ev.t)
     H, W = shape
     ns, nsp = len(segments), len(spans)
-    seg_arr = (_lib.EvSegment * max(ns, 1))()
-    for i, g in enumerate(segments):
-        seg_arr[i] = _lib.EvSegment(int(g[0]), int(g[1]), int(g[2]))
-    span_arr = (_lib.EvSpan * max(nsp, 1))()
-    for i, sp in enumerate(spans):
-        span_arr[i] = _lib.EvSpan(int(sp[0]), int(sp[1]), int(sp[2]), int(sp[3]))
+    keep_seg, seg_arr = _records(segments, _lib.EvSegment)
+    keep_span, span_arr = _records(spans, _lib.EvSpan)
     if out is None and want_f32:
         out = torch.empty((nsp, 2 * K, H, W), dtype=torch.float32, device=ev.device)
     need = _lib.load().evrep_event_volume_spans_scratch_bytes(ev.n, ns, nsp, H, W, K)
@@ -554,7 +559,7 @@ def event_volume_spans(ev: EventStream, segments, spans, shape, K: int, maps=Non
     xm, ym = _maps(maps)
     sensor = maps.sensor_shape if maps is not None else (H, W)
     _lib.call("evrep_event_volume_spans", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
-              ctypes.cast(seg_arr, ctypes.c_void_p), ns, ctypes.cast(span_arr, ctypes.c_void_p), nsp, H, W, K, xm, ym,
+              seg_arr, ns, span_arr, nsp, H, W, K, xm, ym,
               sensor[0], sensor[1], _ptr(out), 2 * K * H * W, _ptr(out_u8), 2 * K * H * W, _ptr(buf), buf.numel(),
               _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
     return out
@@ -596,13 +601,16 @@ def plan_count_segments(windows):
     windows.  Returns ``(segments, order, emits)``: consecutive ``(ev_begin, ev_end)`` segments,
     the indices of the non-empty windows sorted by their last segment, and for each of those (in
     that order) the inclusive run ``(first_segment, last_segment)`` it covers."""
-    live = [i for i, (lo, hi) in enumerate(windows) if hi > lo]
-    bounds = sorted({int(b) for i in live for b in windows[i]})
-    index = {b: k for k, b in enumerate(bounds)}
-    segments = [(bounds[k], bounds[k + 1]) for k in range(len(bounds) - 1)]
-    order = sorted(live, key=lambda i: index[int(windows[i][1])])                 # stable: by last segment
-    emits = [(index[int(windows[i][0])], index[int(windows[i][1])] - 1) for i in order]
-    return segments, order, emits
+    w = np.asarray(windows, dtype=np.int64).reshape(-1, 2)
+    live = np.nonzero(w[:, 1] > w[:, 0])[0]
+    if live.size == 0:
+        return [], [], []
+    bounds = np.unique(w[live])
+    first = np.searchsorted(bounds, w[live, 0])
+    last = np.searchsorted(bounds, w[live, 1]) - 1
+    by_last = np.argsort(last, kind="stable")
+    segments = list(zip(bounds[:-1].tolist(), bounds[1:].tolist()))
+    return segments, live[by_last].tolist(), list(zip(first[by_last].tolist(), last[by_last].tolist()))
 
 
 def count_stream(ev: EventStream, windows, shape, maps=None):
@@ -618,12 +626,8 @@ def count_stream(ev: EventStream, windows, shape, maps=None):
     if not order:
         return frames
     n_seg = len(segments)
-    seg = (_lib.CountSegment * n_seg)()
-    for k, (lo, hi) in enumerate(segments):
-        seg[k] = _lib.CountSegment(lo, hi)
-    emits = (_lib.CountEmit * len(order))()
-    for j, (first, last) in enumerate(runs):
-        emits[j] = _lib.CountEmit(first, last)
+    keep_seg, seg = _records(segments, _lib.CountSegment)
+    keep_emits, emits = _records(runs, _lib.CountEmit)
     out = frames if order == list(range(nw)) else torch.empty((len(order), 2, H, W), dtype=torch.uint8, device=ev.device)
     need = _lib.load().evrep_count_stream_scratch_bytes(ev.n, n_seg, len(order), H, W)
     if need < 0:
@@ -631,7 +635,7 @@ def count_stream(ev: EventStream, windows, shape, maps=None):
     buf = workspace("taf_stream", need, ev.device)
     xm, ym = _maps(maps)
     _lib.call("evrep_count_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
-              ctypes.cast(seg, ctypes.c_void_p), n_seg, ctypes.cast(emits, ctypes.c_void_p), len(order), H, W, xm, ym,
+              seg, n_seg, emits, len(order), H, W, xm, ym,
               maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W,
               _ptr(out), 2 * H * W, _ptr(buf), buf.numel(), _stream(ev.device))
     if out is not frames:
@@ -666,20 +670,18 @@ def sae_stream(ev: EventStream, windows, shape, memory=None, maps=None, out=None
     _need_cuda(ev.t, memory)
     H, W = shape
     nw = len(windows)
-    arr = (_lib.SaeWindow * max(nw, 1))()
-    for i, w in enumerate(windows):
-        arr[i] = _lib.SaeWindow(int(w[0]), int(w[1]), int(w[2]), int(w[3]), int(w[4]))
+    keep, arr = _records([tuple(w[:5]) for w in windows], _lib.SaeWindow)
     if out is None:
         out = torch.empty((nw, 2, H, W), dtype=torch.float32, device=ev.device)
     assert out.is_contiguous()
     state = memory.clone() if memory is not None else torch.empty((2, H, W), dtype=torch.float32, device=ev.device)
-    need = _lib.load().evrep_sae_stream_scratch_bytes(ev.n, ctypes.cast(arr, ctypes.c_void_p), nw, H, W)
+    need = _lib.load().evrep_sae_stream_scratch_bytes(ev.n, arr, nw, H, W)
     if need < 0:
         _lib.check(int(need), "evrep_sae_stream_scratch_bytes")
     buf = workspace("taf_stream", need, ev.device)
     xm, ym = _maps(maps)
     _lib.call("evrep_sae_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
-              ctypes.cast(arr, ctypes.c_void_p), nw, H, W, xm, ym,
+              arr, nw, H, W, xm, ym,
               maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W,
               _ptr(state), 1 if memory is not None else 0, _ptr(out), 2 * H * W, _ptr(buf), buf.numel(), _stream(ev.device))
     return out, state
