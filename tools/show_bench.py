@@ -4,4 +4,4 @@ print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], d["
 print("roofline", d["roofline"]["frac"], d["roofline"]["step_frac"], d["roofline"]["kernel_ms"])
 print("parity", d["parity_check"])
 print("ev", {k:v for k,v in d["ev"].items() if k!="path"})
-print("cpu", d["cpu_baseline"]["value"], "clocks", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+print("cpu", (d["cpu_baseline"] or {}).get("value"), "clocks", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
