@@ -81,13 +81,19 @@ def nearest_maps(in_shape, out_shape, device):
 
 
 # ------------------------------------------------------------------------- scratch
+def _dev_index(device) -> int:
+    device = torch.device(device)
+    return torch.cuda.current_device() if device.index is None else device.index
+
+
 _scratch = {}
 
 
 def scratch(kind: str, nbytes: int, device) -> torch.Tensor:
-    """Zero-initialised scratch, cached per (device, kind, size).  All kernels leave
-    their scratch zeroed on return, so one allocation serves every call."""
-    key = (str(device), kind, int(nbytes))
+    """Zero-initialised scratch, cached per (device, kind, size, current stream): two streams never share
+    accumulators.  Every kernel leaves its scratch zeroed on return, so one allocation serves every call;
+    a call that fails may not have, which is why ``_call`` wipes the cache's buffers before it re-raises."""
+    key = (_dev_index(device), kind, int(nbytes), torch.cuda.current_stream(device).cuda_stream)
     buf = _scratch.get(key)
     if buf is None:
         buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
@@ -95,12 +101,17 @@ def scratch(kind: str, nbytes: int, device) -> torch.Tensor:
     return buf
 
 
+def _call(name: str, *args):
+    """``_lib.call`` for the entry points that use ``scratch`` buffers: a failed call may leave counters behind."""
+    try:
+        _lib.call(name, *args)
+    except _lib.EvrepError:
+        for buf in _scratch.values():
+            buf.zero_()
+        raise
+
+
 _workspace = {}
-
-
-def _dev_index(device) -> int:
-    device = torch.device(device)
-    return torch.cuda.current_device() if device.index is None else device.index
 
 
 def workspace(kind: str, nbytes: int, device) -> torch.Tensor:
@@ -139,7 +150,7 @@ class EventStream:
         ``*_ordered`` entry points of the library need it."""
         if self.ordered is None:
             flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-            _lib.call("evrep_events_order_check", _ptr(self.t), self.n, _ptr(flag), _stream(self.device))
+            _call("evrep_events_order_check", _ptr(self.t), self.n, _ptr(flag), _stream(self.device))
             self.ordered = int(flag.item()) == 0
         return self.ordered
 
@@ -164,7 +175,7 @@ class EventStream:
     def to_aos64(self) -> torch.Tensor:
         """The reference's staging matrix: float64 ``[n,4]`` columns (x, y, t, p)."""
         out = torch.empty((self.n, 4), dtype=torch.float64, device=self.device)
-        _lib.call("evrep_soa_to_aos64", _ptr(self.t), _ptr(self.x), _ptr(self.y), _ptr(self.p),
+        _call("evrep_soa_to_aos64", _ptr(self.t), _ptr(self.x), _ptr(self.y), _ptr(self.p),
                   self.n, _ptr(out), _stream(self.device))
         return out
 
@@ -176,7 +187,7 @@ def decode_dat(records: torch.Tensor, out: Optional[EventStream] = None) -> Even
     n = records.numel() // 8
     ev = out if out is not None else EventStream.empty(n, records.device)
     assert ev.n == n
-    _lib.call("evrep_decode_dat", _ptr(records), n, _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p),
+    _call("evrep_decode_dat", _ptr(records), n, _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p),
               _stream(records.device))
     return ev
 
@@ -191,7 +202,7 @@ def count_accumulate(ev: EventStream, shape, maps=None, counts=None) -> torch.Te
     if counts is None:
         counts = scratch("count", 8 * H * W, ev.device).view(torch.int32)
     xm, ym = _maps(maps)
-    _lib.call("evrep_count_accumulate", _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, H, W, xm, ym,
+    _call("evrep_count_accumulate", _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, H, W, xm, ym,
               _ptr(counts), _stream(ev.device))
     return counts
 
@@ -200,7 +211,7 @@ def count_finalize(counts, shape, reset=True, out=None) -> torch.Tensor:
     H, W = shape
     if out is None:
         out = torch.empty((2, H, W), dtype=torch.float32, device=counts.device)
-    _lib.call("evrep_count_finalize", _ptr(counts), H, W, _ptr(out), int(bool(reset)), _stream(counts.device))
+    _call("evrep_count_finalize", _ptr(counts), H, W, _ptr(out), int(bool(reset)), _stream(counts.device))
     return out
 
 
@@ -233,7 +244,7 @@ def count_image_aos64(events: torch.Tensor, shape) -> torch.Tensor:
     H, W = shape
     events = events.contiguous()
     counts = scratch("count", 8 * H * W, events.device).view(torch.int32)
-    _lib.call("evrep_count_accumulate_aos64", _ptr(events), events.shape[0], events.shape[1], H, W,
+    _call("evrep_count_accumulate_aos64", _ptr(events), events.shape[0], events.shape[1], H, W,
               _ptr(counts), _stream(events.device))
     return count_finalize(counts, shape, True)
 
@@ -255,7 +266,7 @@ def sae(ev: EventStream, shape, lambdas, memory, now, maps=None):
     mem_out = torch.empty((2, H, W), dtype=torch.float32, device=ev.device)
     keys = scratch("sae", 8 * H * W, ev.device)
     xm, ym = _maps(maps)
-    _lib.call("evrep_sae", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, H, W, xm, ym, init, now_f32,
+    _call("evrep_sae", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, H, W, xm, ym, init, now_f32,
               ctypes.cast(lam, ctypes.c_void_p), L, _ptr(memory), _ptr(mem_out), _ptr(keys), _ptr(out),
               _stream(ev.device))
     return out, mem_out
@@ -271,7 +282,7 @@ def sae_aos64(events, shape, lambdas, memory, now):
     out = torch.empty((2 * L, H, W), dtype=torch.float32, device=events.device)
     mem_out = torch.empty((2, H, W), dtype=torch.float32, device=events.device)
     keys = scratch("sae", 8 * H * W, events.device)
-    _lib.call("evrep_sae_aos64", _ptr(events), events.shape[0], events.shape[1], H, W, init, now_f32,
+    _call("evrep_sae_aos64", _ptr(events), events.shape[0], events.shape[1], H, W, init, now_f32,
               ctypes.cast(lam, ctypes.c_void_p), L, _ptr(memory), _ptr(mem_out), _ptr(keys), _ptr(out),
               _stream(events.device))
     return out, mem_out
@@ -284,7 +295,7 @@ def event_volume(ev: EventStream, t0: int, tw: int, shape, K: int, maps=None, ou
     if out is None:
         out = torch.empty((2 * K, H, W), dtype=torch.float32, device=ev.device)
     xm, ym = _maps(maps)
-    _lib.call("evrep_event_volume", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, int(t0), int(tw),
+    _call("evrep_event_volume", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, int(t0), int(tw),
               H, W, K, xm, ym, _ptr(out), _stream(ev.device))
     return out
 
@@ -294,7 +305,7 @@ def event_volume_aos64(events, shape, K: int):
     H, W = shape
     events = events.contiguous()
     out = torch.empty((2 * K, H, W), dtype=torch.float32, device=events.device)
-    _lib.call("evrep_event_volume_aos64", _ptr(events), events.shape[0], events.shape[1], H, W, K, _ptr(out),
+    _call("evrep_event_volume_aos64", _ptr(events), events.shape[0], events.shape[1], H, W, K, _ptr(out),
               _stream(events.device))
     return out
 
@@ -317,7 +328,7 @@ def taf_bin(ev: EventStream, t_min: int, t_span: float, shape, K: int, state, ma
     new_state = state if in_place else torch.empty_like(state)
     out = torch.empty((2 * K, H, W), dtype=torch.float32, device=state.device) if want_out else None
     xm, ym = _maps(maps)
-    _lib.call("evrep_taf_bin", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, int(t_min), float(t_span),
+    _call("evrep_taf_bin", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, int(t_min), float(t_span),
               H, W, K, xm, ym, _ptr(state), _ptr(new_state), _ptr(out), _ptr(_taf_scratch(shape, state.device)),
               _stream(state.device))
     return out, new_state
@@ -330,7 +341,7 @@ def taf_bin_aos64(events, shape, K: int, state):
     state = state.contiguous()
     new_state = torch.empty_like(state)
     out = torch.empty((2 * K, H, W), dtype=torch.float32, device=state.device)
-    _lib.call("evrep_taf_bin_aos64", _ptr(events), events.shape[0], events.shape[1] if events.dim() == 2 else 5,
+    _call("evrep_taf_bin_aos64", _ptr(events), events.shape[0], events.shape[1] if events.dim() == 2 else 5,
               H, W, K, _ptr(state), _ptr(new_state), _ptr(out), _ptr(_taf_scratch(shape, state.device)),
               _stream(state.device))
     return out, new_state
@@ -369,7 +380,7 @@ def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=N
         buf = workspace("taf_ordered", need, ev.device)
         if out_u8 is not None:
             assert out_u8.is_contiguous() and out_u8.dtype == torch.uint8 and out_u8.numel() >= nw * 2 * K * H * W
-        _lib.call("evrep_taf_stream_ordered", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+        _call("evrep_taf_stream_ordered", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
                   arr, nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
                   int(bool(emit_state_every_window)), _ptr(out), 2 * K * H * W, _ptr(out_u8), 2 * K * H * W,
                   _ptr(buf), buf.numel(),
@@ -380,7 +391,7 @@ def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=N
         _lib.check(int(need), "evrep_taf_stream_scratch_bytes")
     buf = workspace("taf_stream", need, ev.device)
     vol = out if out is not None else torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=ev.device)
-    _lib.call("evrep_taf_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+    _call("evrep_taf_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
               arr, nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
               int(bool(emit_state_every_window)), _ptr(vol), 2 * K * H * W, _ptr(buf), buf.numel(),
               _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
@@ -401,7 +412,7 @@ def order_violations(device) -> int:
     if buf is None:
         return 0
     host = ctypes.c_uint32(0)
-    _lib.call("evrep_stream_order_violations", _ptr(buf), ctypes.byref(host), _stream(buf.device))
+    _call("evrep_stream_order_violations", _ptr(buf), ctypes.byref(host), _stream(buf.device))
     return int(host.value)
 
 
@@ -421,7 +432,7 @@ def nearest_resize(volume, target_shape, maps=None):
     Ht, Wt = target_shape
     ys, xs = maps if maps is not None else nearest_maps((H, W), (Ht, Wt), volume.device)
     out = torch.empty((C, Ht, Wt), dtype=torch.float32, device=volume.device)
-    _lib.call("evrep_nearest_resize", _ptr(volume.contiguous()), C, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
+    _call("evrep_nearest_resize", _ptr(volume.contiguous()), C, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
               _stream(volume.device))
     return out
 
@@ -431,7 +442,7 @@ def quantize_u8(volume, clamp255=False, out=None):
     volume = volume.contiguous()
     if out is None:
         out = torch.empty(volume.shape, dtype=torch.uint8, device=volume.device)
-    _lib.call("evrep_quantize_u8", _ptr(volume), volume.numel(), int(bool(clamp255)), _ptr(out), _stream(volume.device))
+    _call("evrep_quantize_u8", _ptr(volume), volume.numel(), int(bool(clamp255)), _ptr(out), _stream(volume.device))
     return out
 
 
@@ -439,7 +450,7 @@ def leaky_transform(ecd):
     _need_cuda(ecd)
     src = ecd.contiguous()
     out = torch.empty_like(src)
-    _lib.call("evrep_leaky_transform", _ptr(src), src.numel(), _ptr(out), _stream(src.device))
+    _call("evrep_leaky_transform", _ptr(src), src.numel(), _ptr(out), _stream(src.device))
     return out
 
 
@@ -454,7 +465,7 @@ def taf_leaky_u8(volume, K: int, target_shape=None, maps=None, out=None):
     ys, xs = maps if maps is not None else (None, None)
     if out is None:
         out = torch.empty((K, 2, Ht, Wt), dtype=torch.uint8, device=volume.device)
-    _lib.call("evrep_taf_leaky_u8", _ptr(volume.contiguous()), K, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
+    _call("evrep_taf_leaky_u8", _ptr(volume.contiguous()), K, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
               _stream(volume.device))
     return out
 
@@ -470,7 +481,7 @@ def taf_leaky_u8_batch(volumes, K: int, target_shape=None, maps=None, out=None):
     ys, xs = maps if maps is not None else (None, None)
     if out is None:
         out = torch.empty((n, K, 2, Ht, Wt), dtype=torch.uint8, device=volumes.device)
-    _lib.call("evrep_taf_leaky_u8_batch", _ptr(volumes), C * H * W, n, K, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
+    _call("evrep_taf_leaky_u8_batch", _ptr(volumes), C * H * W, n, K, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
               _stream(volumes.device))
     return out
 
@@ -490,7 +501,7 @@ def event_volume_stream(ev: EventStream, windows, tw: int, shape, K: int, maps=N
         _lib.check(int(need), "evrep_event_volume_stream_scratch_bytes")
     buf = workspace("taf_stream", need, ev.device)
     xm, ym = _maps(maps)
-    _lib.call("evrep_event_volume_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+    _call("evrep_event_volume_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
               arr, nw, int(tw), H, W, K, xm, ym,
               maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W,
               _ptr(out), 2 * K * H * W, _ptr(buf), buf.numel(), _stream(ev.device))
@@ -558,7 +569,7 @@ def event_volume_spans(ev: EventStream, segments, spans, shape, K: int, maps=Non
     buf = workspace("ev_spans", need, ev.device)
     xm, ym = _maps(maps)
     sensor = maps.sensor_shape if maps is not None else (H, W)
-    _lib.call("evrep_event_volume_spans", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+    _call("evrep_event_volume_spans", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
               seg_arr, ns, span_arr, nsp, H, W, K, xm, ym,
               sensor[0], sensor[1], _ptr(out), 2 * K * H * W, _ptr(out_u8), 2 * K * H * W, _ptr(buf), buf.numel(),
               _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
@@ -577,7 +588,7 @@ def event_volume_u8_batch(volumes, target_shape=None, maps=None, out=None):
     ys, xs = maps if (maps is not None and (Ht, Wt) != (H, W)) else (None, None)
     if out is None:
         out = torch.empty((n, C, Ht, Wt), dtype=torch.uint8, device=volumes.device)
-    _lib.call("evrep_event_volume_u8_batch", _ptr(volumes), C * H * W, n, C, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
+    _call("evrep_event_volume_u8_batch", _ptr(volumes), C * H * W, n, C, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
               _stream(volumes.device))
     return out
 
@@ -591,7 +602,7 @@ def timesurface(ev: EventStream, shape):
     out_old = torch.empty((H, W), dtype=torch.float64, device=ev.device)
     out_all = torch.empty((H, W), dtype=torch.float64, device=ev.device)
     buf = scratch("timesurface", _lib.load().evrep_timesurface_scratch_bytes(H, W), ev.device)
-    _lib.call("evrep_timesurface", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), ev.n, H, W, _ptr(buf), _ptr(out_old), _ptr(out_all),
+    _call("evrep_timesurface", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), ev.n, H, W, _ptr(buf), _ptr(out_old), _ptr(out_all),
               _stream(ev.device))
     return out_old, out_all
 
@@ -634,7 +645,7 @@ def count_stream(ev: EventStream, windows, shape, maps=None):
         _lib.check(int(need), "evrep_count_stream_scratch_bytes")
     buf = workspace("taf_stream", need, ev.device)
     xm, ym = _maps(maps)
-    _lib.call("evrep_count_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+    _call("evrep_count_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
               seg, n_seg, emits, len(order), H, W, xm, ym,
               maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W,
               _ptr(out), 2 * H * W, _ptr(buf), buf.numel(), _stream(ev.device))
@@ -655,7 +666,7 @@ def count_lut_u8_batch(frames, target_shape=None, resize_maps=None, out=None):
     ys, xs = resize_maps if (Ht, Wt) != (H, W) else (None, None)
     if out is None:
         out = torch.empty((n, 2, Ht, Wt), dtype=torch.uint8, device=frames.device)
-    _lib.call("evrep_count_lut_u8_batch", _ptr(frames), 2 * H * W, n, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
+    _call("evrep_count_lut_u8_batch", _ptr(frames), 2 * H * W, n, H, W, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(out),
               _stream(frames.device))
     return out
 
@@ -680,7 +691,7 @@ def sae_stream(ev: EventStream, windows, shape, memory=None, maps=None, out=None
         _lib.check(int(need), "evrep_sae_stream_scratch_bytes")
     buf = workspace("taf_stream", need, ev.device)
     xm, ym = _maps(maps)
-    _lib.call("evrep_sae_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+    _call("evrep_sae_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
               arr, nw, H, W, xm, ym,
               maps.sensor_shape[0] if maps is not None else H, maps.sensor_shape[1] if maps is not None else W,
               _ptr(state), 1 if memory is not None else 0, _ptr(out), 2 * H * W, _ptr(buf), buf.numel(), _stream(ev.device))
@@ -702,7 +713,7 @@ def sae_decay_u8_batch(latest, nows, lambdas, target_shape=None, resize_maps=Non
     now_f32 = torch.from_numpy(np.asarray([float(v) for v in nows], dtype=np.float64).astype(np.float32)).to(latest.device)
     if out is None:
         out = torch.empty((n, L, 2, Ht, Wt), dtype=torch.uint8, device=latest.device)
-    _lib.call("evrep_sae_decay_u8_batch", _ptr(latest), 2 * H * W, _ptr(now_f32), n, H, W, Ht, Wt, _ptr(ys), _ptr(xs),
+    _call("evrep_sae_decay_u8_batch", _ptr(latest), 2 * H * W, _ptr(now_f32), n, H, W, Ht, Wt, _ptr(ys), _ptr(xs),
               ctypes.cast(lam, ctypes.c_void_p), L, _ptr(out), _stream(latest.device))
     return out
 
@@ -722,7 +733,7 @@ def count_images_u8(ev: EventStream, sizes: Sequence[int], shape, target_shape, 
         out = torch.empty((len(sizes), 2, Ht, Wt), dtype=torch.uint8, device=ev.device)
     counts = scratch("count", 8 * H * W, ev.device)
     xm, ym = _maps(maps)
-    _lib.call("evrep_count_images_u8", _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, ctypes.cast(arr, ctypes.c_void_p),
+    _call("evrep_count_images_u8", _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, ctypes.cast(arr, ctypes.c_void_p),
               len(sizes), H, W, xm, ym, Ht, Wt, _ptr(ys), _ptr(xs), _ptr(counts), _ptr(out), _stream(ev.device))
     return out
 
@@ -743,7 +754,7 @@ def sae_u8(ev: EventStream, shape, target_shape, lambdas, memory, now, maps=None
     mem_out = torch.empty((2, H, W), dtype=torch.float32, device=ev.device)
     keys = scratch("sae", 8 * H * W, ev.device)
     xm, ym = _maps(maps)
-    _lib.call("evrep_sae_u8", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, H, W, xm, ym, Ht, Wt, _ptr(ys), _ptr(xs),
+    _call("evrep_sae_u8", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n, H, W, xm, ym, Ht, Wt, _ptr(ys), _ptr(xs),
               init, now_f32, ctypes.cast(lam, ctypes.c_void_p), L, _ptr(memory), _ptr(mem_out), _ptr(keys), _ptr(out),
               _stream(ev.device))
     return out, mem_out
