@@ -88,6 +88,13 @@ def main():
     emit(config="2: SAE driver, whole-stream kernel (256 labels per call), GEN1 %gs" % args.gen1_seconds, events=n,
          labels=len(labels), ms=s * 1e3, labels_per_s=len(labels) / s, Mevents_per_s=n / s / 1e6,
          frac_of_measured_peak=algo / s / 1e9 / peak)
+    # Event Volume driver (generate_eventvolume.py:118-169): 250 / 500 / 1000 ms windows per label, K = 5
+    from frlw_evd_b200 import generate_eventvolume as g_ev
+    plan = g_ev.label_windows(rec.loader, labels)
+    splats = sum(hi - lo for _, ws in plan for lo, hi, _, _ in ws)
+    s = wall(lambda: [None for _ in g_ev.encode_recording(rec, labels, geom)], reps=2)
+    emit(config="V2: Event Volume driver (250/500/1000 ms per label, K=5, span kernels), GEN1 %gs" % args.gen1_seconds, events=n,
+         labels=len(plan), window_events=splats, ms=s * 1e3, labels_per_s=len(plan) / s, window_Mevents_per_s=splats / s / 1e6)
     del rec
 
     # ---- 1MP (config 4): TAF K=4 next to the headline K=8, native-grid variant
@@ -109,6 +116,18 @@ def main():
         emit(config="4: TAF K=%d, 1MP on %dx%d grid" % (K, grid[0], grid[1]), events=nev, windows=nw, ms=s * 1e3,
              Mevents_per_s=nev / s / 1e6, frac_of_measured_peak=algo / s / 1e9 / peak)
         del out
+
+
+    # Event Volume driver on the 1MP stream, gen4 policy (the windows of a label hold up to 10 M events)
+    from frlw_evd_b200 import generate_eventvolume as g_ev
+    rec = Rec(t, x, y, p, dev)
+    geom4 = Geometry.for_dataset("gen4")
+    labels4 = synth.label_times(10_000_000)
+    plan = g_ev.label_windows(rec.loader, labels4)
+    splats = sum(hi - lo for _, ws in plan for lo, hi, _, _ in ws)
+    s = wall(lambda: [None for _ in g_ev.encode_recording(rec, labels4, geom4)], reps=2)
+    emit(config="V2: Event Volume driver (250/500/1000 ms per label, K=5, span kernels), 1MP 10s gen4 policy", events=n,
+         labels=len(plan), window_events=splats, ms=s * 1e3, labels_per_s=len(plan) / s, window_Mevents_per_s=splats / s / 1e6)
 
 
 if __name__ == "__main__":
