@@ -75,44 +75,38 @@ def encode_one(rep: str, dataset: str, mode: str, name: str, event_file: str, la
     from . import generate_surfaceofactiveevents as sae
     from . import generate_taf as taf
     from .io import npy_events_tools
-    from .recordings import DeviceRecording, Geometry, dump_u8
+    from .recordings import AsyncWriter, DeviceRecording, Geometry, PinnedRing
 
     geom = Geometry.for_dataset(dataset)
     labels = npy_events_tools.read_label_times(label_file)
-    if rep == "taf":                      # host pipeline: H2D, kernels and D2H overlap, files written by a thread pool
-        from .recordings import AsyncWriter
+    writer = AsyncWriter()              # files are written by a thread pool behind a ring of pinned buffers
+    if rep == "taf":                    # host pipeline: H2D, kernels and D2H overlap
         rec = DeviceRecording(event_file, decode=False)
-        writer = AsyncWriter()
         windows = taf.encode_recording_to_files(rec, labels, name, mode, target_dir, geom, writer)
         writer.close()
         return {"events": rec.n_events, "windows": windows, "bytes_written": writer.bytes_written}
     rec = DeviceRecording(event_file)
-    windows = written = 0
-
-    def put(u8, *path):
-        nonlocal written
-        dump_u8(u8, *path)
-        written += u8.numel()
-
-    if rep == "count_image":
-        sizes = eci.windows_for(dataset)
-        for label, frames in eci.encode_recording_stream(rec, labels, geom, sizes):
-            for n, u8 in zip(sizes, frames):
-                put(u8, target_dir, "EventCountImage{0}".format(n), mode, name + "_" + str(label) + ".npy")
-            windows += 1
-    elif rep == "sae":
-        for label, u8 in sae.encode_recording_stream(rec, labels, geom):
-            for j, lam in enumerate(sae.LAMDAS):
-                put(u8[j], target_dir, "SurfaceOfActiveEvents{0}".format(lam), mode, name + "_" + str(label) + ".npy")
-            windows += 1
-    elif rep == "event_volume":
-        for label, outs in evol.encode_recording(rec, labels, geom):
-            for tw, u8 in zip(evol.TIME_WINDOWS, outs):
-                put(u8, target_dir, "EventVolume{0}".format(tw), mode, name + "_" + str(label) + ".npy")
-            windows += 1
+    ring = PinnedRing(rec.events.device)
+    windows = 0
+    if rep == "event_volume":
+        windows = evol.encode_recording_to_files(rec, labels, name, mode, target_dir, geom, ring, writer)
+    elif rep in ("count_image", "sae"):
+        if rep == "count_image":
+            sizes = eci.windows_for(dataset)
+            chunks, folders = eci.encode_chunks(rec, labels, geom, sizes), ["EventCountImage{0}".format(n) for n in sizes]
+        else:
+            chunks, folders = sae.encode_chunks(rec, labels, geom), ["SurfaceOfActiveEvents{0}".format(lam) for lam in sae.LAMDAS]
+        for chunk_labels, u8 in chunks:
+            def emit(host, names=[name + "_" + str(label) + ".npy" for label in chunk_labels]):
+                return [writer.put(host[i, k], target_dir, folder, mode, fname)
+                        for i, fname in enumerate(names) for k, folder in enumerate(folders)]
+            ring.push(u8.contiguous(), emit)
+            windows += len(chunk_labels)
     else:
         raise ValueError("unknown representation " + rep)
-    return {"events": rec.events.n, "windows": windows, "bytes_written": written}
+    ring.flush()
+    writer.close()
+    return {"events": rec.events.n, "windows": windows, "bytes_written": writer.bytes_written}
 
 
 def run(recordings, encode: Callable[..., dict], device, rank: int, world: int) -> dict:

@@ -57,3 +57,19 @@ def test_driver_files(case, rep, tmp_path):
         assert mg._digest_tree(got_dir) == digests          # byte-identical to the reference's own files
     else:
         assert flips / total < 1e-3, (flips, total)
+
+
+@pytest.mark.parametrize("rep", ["count_image", "sae", "event_volume", "taf"])
+def test_multi_gpu_worker_writes_the_same_files(rep, tmp_path):
+    """`multi_gpu.encode_one` (what every rank runs for its recordings) == the command line, file by file."""
+    from frlw_evd_b200 import multi_gpu
+    case = mg.DRIVER_CASES[0]
+    raw = str(tmp_path / "raw")
+    mg.write_case(raw, case)
+    cli_dir, rank_dir = str(tmp_path / "cli"), str(tmp_path / "rank")
+    PRODUCT[rep](["-raw_dir", raw, "-label_dir", raw, "-target_dir", cli_dir, "-dataset", case[2]])
+    stats = [multi_gpu.encode_one(rep, case[2], mode, name, event_file, label_file, rank_dir)
+             for mode, name, event_file, label_file, _size in multi_gpu.list_recordings(raw, raw)]
+    assert mg._digest_tree(cli_dir) == mg._digest_tree(rank_dir)
+    written = sum(os.path.getsize(p) for p in tree(rank_dir).values())
+    assert sum(s["bytes_written"] for s in stats) == written and all(s["windows"] > 0 for s in stats)
