@@ -118,3 +118,15 @@ def test_driver_chunks_agree(tmp_path):
     assert len(a) == len(b) > 0
     for (la, ua), (lb, ub) in zip(a, b):
         assert la == lb and torch.equal(ua, ub) and ua.shape == (3, 10, 256, 320)
+
+
+def test_only_empty_windows():
+    H, W, K = 32, 48, 5
+    t = np.arange(0, 1000, dtype=np.uint32)
+    z = np.zeros(1000, dtype=np.uint16)
+    ev = ops.EventStream.from_numpy(t, z, z, z.astype(np.uint8))
+    segments, spans = ops.plan_ev_spans([(5, 5, 0, 1000), (900, 900, 100, 50)], *host_index(t))
+    assert segments == [] and spans == [(0, -1, 0, 1000), (0, -1, 100, 50)]
+    u8 = torch.full((2, 2 * K, H, W), 7, dtype=torch.uint8, device=DEV)
+    got = ops.event_volume_spans(ev, segments, spans, (H, W), K, out_u8=u8)
+    assert float(got.abs().max()) == 0.0 and int(u8.max()) == 0

@@ -203,3 +203,23 @@ def test_long_window_rebases_inside(ordered_path):
     state = ops.taf_fresh_state((H, W), K, DEV)
     got = ops.taf_stream(ev, windows, abin, (H, W), K, state)
     assert close(got[0], want[0]) and close(state, want_state)
+
+
+def test_degenerate_inputs(ordered_path):
+    """Windows without bins, windows without events, an empty stream: the state is emitted unchanged."""
+    H, W, K = 16, 24, 8
+    t = np.arange(0, 5000, 5, dtype=np.uint32)
+    n = len(t)
+    x = (np.arange(n) % W).astype(np.uint16); y = (np.arange(n) % H).astype(np.uint16); p = (np.arange(n) % 2).astype(np.uint8)
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    state = ops.taf_fresh_state((H, W), K, DEV)
+    state += torch.arange(K, device=DEV, dtype=torch.float32)                # something recognisable
+    before = state.clone()
+    out = ops.taf_stream(ev, [(0, 0, 0, 0, 0), (0, 0, 0, 0, 0)], 1000, (H, W), K, state)       # no bins at all
+    want = before.permute(3, 2, 0, 1).reshape(2 * K, H, W)
+    assert torch.equal(out[0], want) and torch.equal(out[1], want) and torch.equal(state, before)
+    out = ops.taf_stream(ev, [(n, n, 9000, 3, 0)], 1000, (H, W), K, state)                     # bins, but no events in them
+    assert torch.equal(out[0], want) and torch.equal(state, before)
+    empty = ops.EventStream.from_numpy(t[:0], x[:0], y[:0], p[:0])
+    out = ops.taf_stream(empty, [(0, 0, 0, 2, 1)], 1000, (H, W), K, state)                     # fresh window on an empty stream
+    assert torch.equal(out[0], torch.full((2 * K, H, W), -6000.0, device=DEV))
