@@ -389,7 +389,7 @@ def main():
         from frlw_evd_b200.recordings import Geometry
         geom = Geometry((720, 1280), GRID, dev, coord_maps=maps)
         raw_host = torch.from_numpy(records.view(np.uint8)).pin_memory()
-        pipe = gt.HostPipeline(geom, windows, K, ABIN, windows_per_chunk=12, device=dev)
+        pipe = gt.HostPipeline(geom, windows, K, ABIN, device=dev)
         u8_host = torch.empty(pipe.out_shape, dtype=torch.uint8).pin_memory()
 
         def e2e_step():
@@ -420,7 +420,7 @@ def main():
                "copy_floor_ms": floor_ms, "copy_floor_note": "the step's bytes, both directions at once, all ranks at once, no kernels",
                "h2d_bytes_per_step": int(raw_host.numel()), "d2h_bytes_per_step": int(u8_host.numel()),
                "path": "pinned .dat bytes -> H2D -> decode -> taf_stream -> leaky uint8 [K,2,Ht,Wt] -> D2H, "
-                       "12-window chunks on three streams (generate_taf.HostPipeline)"}
+                       "1/2/4/8-window chunks on three streams (generate_taf.HostPipeline)"}
 
     sampler.stop()
     clocks = sampler.report("device")
