@@ -77,8 +77,12 @@ SIGNATURES = {
     "evrep_taf_stream_scratch_bytes": (c_int64, [c_int64, c_int, c_int64, c_int, c_int]),
     "evrep_taf_stream": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int,
                                  P, c_int64, P, c_int64, P, P, P]),
-    "evrep_taf_stream_ordered_scratch_bytes": (c_int64, [c_int64, c_int, c_int64, c_int, c_int, c_int]),
-    "evrep_taf_stream_ordered": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P,
+    "evrep_taf_stream_ordered_scratch_bytes": (c_int64, [c_int64, c_int, c_int64, c_int, c_int]),
+    "evrep_taf_stream_ordered_status_offset": (c_int64, [c_int64, c_int, c_int64, c_int, c_int]),
+    "evrep_taf_stream_ordered": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int,
+                                         P, c_int64, P, c_int64, P, P, P]),
+    "evrep_taf_stream_sliced_scratch_bytes": (c_int64, [c_int64, c_int, c_int64, c_int, c_int, c_int]),
+    "evrep_taf_stream_sliced": (c_int, [P, P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P,
                                          c_int, P, c_int64, P, c_int64, P, c_int64, P, P, P]),
     "evrep_stream_order_violations": (c_int, [P, P, P]),
     "evrep_events_order_check": (c_int, [P, c_int64, P, P]),

@@ -3,7 +3,7 @@
 // d = t - bin start.  Count (shared-memory histograms per 4096-event chunk), scan (per tile
 // row, then across tiles), scatter (records ordered in shared memory, runs written with
 // consecutive addresses).  Also the host-side front end shared by the stream entry points.
-#include "stream_common.cuh"
+#include "slices.cuh"
 
 namespace evrep {
 
@@ -776,6 +776,175 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
         EVREP_CUDA(cudaMemsetAsync(s + L.o_tiletotal, 0, (size_t)(L.o_origins - L.o_tiletotal), st));   // totals, bases, tile bits
     }
 
+    return EVREP_OK;
+}
+
+// ---- time-ordered input: one-pass bin-major sort (slices.cu) in front of the same tile kernels ----------------------
+// Same tables as prepare_stream (counts -> off_rel / tile_total, bin_any, tile_bits, batches), but the records come from
+// the slice sort's bin-major mode: every (bin, tile) run contiguous at src[tile][bin], padded to 16 bytes with null
+// records; off_rel counts the padded records.  Windows of more than kBinMajorMaxParts slices are refused (their bins'
+// slices might not all be resident at once): the caller uses prepare_stream for those.
+struct BinMajorLayout {
+    Layout L;
+    int64_t o_status, o_wfresh, o_src, o_bins, o_slicebin, o_cnt16, o_bindone, total;
+    int64_t max_slices;
+    int pitch16;
+};
+
+static int make_binmajor_layout(int64_t n_events, int n_windows, int64_t TB, int H, int W, int n_batches, BinMajorLayout& B) {
+    Layout& L = B.L;
+    int rc = make_layout(0, n_windows, TB, H, W, n_batches, L);          // tile geometry and the table offsets; records re-sized below
+    if (rc) return rc;
+    if (n_events >= (1ll << 31) || n_events + (4ll * L.n_tiles + 3) * TB >= (1ll << 32)) return EVREP_ERR_RANGE;
+    B.max_slices = n_events / kSliceMax + TB + 1;
+    B.pitch16 = (L.n_tiles + 7) / 8 * 8;
+    int64_t o = L.o_origins;                                              // the two-pass scratch (origins, saved records) is not needed
+    L.o_records = o;  o += align_up(4ll * (n_events + (4ll * L.n_tiles + 3) * TB + 64), 256);   // per bin: events rounded up to 4 + 4 per tile
+    B.o_status = o;   o += 256;
+    B.o_wfresh = o;   o += align_up(4ll * (n_windows + 1), 256);
+    B.o_src = o;      o += align_up(4ll * L.n_tiles * (TB > 0 ? TB : 1), 256);
+    B.o_bins = o;     o += align_up((int64_t)sizeof(BinDesc) * (TB > 0 ? TB : 1), 256);
+    B.o_slicebin = o; o += align_up(4ll * B.max_slices, 256);
+    B.o_cnt16 = o;    o += align_up(2ll * B.max_slices * B.pitch16, 256);
+    B.o_bindone = o;  o += align_up(4ll * (TB > 0 ? TB : 1), 256);
+    B.total = o;
+    L.total = o;
+    return EVREP_OK;
+}
+
+int64_t binmajor_status_offset(int64_t n_events, int n_windows, int64_t TB, int H, int W) {
+    BinMajorLayout B;
+    int rc = make_binmajor_layout(n_events, n_windows, TB, H, W, (int)batches_upper_bound(n_windows, TB), B);
+    return rc ? rc : B.o_status;
+}
+
+int64_t binmajor_scratch_bytes(int64_t n_events, int n_windows, int64_t TB, int H, int W) {
+    BinMajorLayout B;
+    int rc = make_binmajor_layout(n_events, n_windows, TB, H, W, (int)batches_upper_bound(n_windows, TB), B);
+    return rc ? rc : B.total;
+}
+
+int prepare_stream_binmajor(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+                            const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W,
+                            const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                            void* scratch, int64_t scratch_bytes, cudaStream_t st, StreamPlan& pl, Layout& L_out,
+                            const uint32_t*& src_out, uint32_t*& status_out) {
+    if (xmap && ymap && (sensor_h <= 0 || sensor_w <= 0 || sensor_h > EVREP_COORD_LUT_LEN || sensor_w > EVREP_COORD_LUT_LEN))
+        return EVREP_ERR_ARG;
+    if (abin <= 0 || (uint32_t)abin > kDMax) return EVREP_ERR_RANGE;
+    if (!windows_host || (n_events > 0 && (!t || !x || !y || !p))) return EVREP_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(scratch) & 255) return EVREP_ERR_ARG;
+    int64_t TB = 0, prev_end = 0;
+    for (int w = 0; w < n_windows; ++w) {
+        const evrep_taf_window& win = windows_host[w];
+        if (win.ev_begin < prev_end || win.ev_end < win.ev_begin || win.ev_end > n_events || win.n_bins < 0) return EVREP_ERR_ARG;
+        if ((int64_t)win.n_bins * abin >= (1ll << 32)) return EVREP_ERR_RANGE;
+        if (win.ev_end - win.ev_begin > (int64_t)kBinMajorMaxParts * kSliceMax) return EVREP_ERR_RANGE;   // a bin could exceed the resident CTAs
+        prev_end = win.ev_end;
+        TB += win.n_bins;
+    }
+    std::vector<Batch> batches;
+    batches.reserve((size_t)batches_upper_bound(n_windows, TB));
+    {
+        int gbin = 0;
+        for (int w = 0; w < n_windows; ++w) {
+            const int nb = windows_host[w].n_bins;
+            int done = 0;
+            do {
+                Batch b;
+                b.gbin0 = gbin + done;
+                b.nb = nb - done < kBatchBins ? nb - done : kBatchBins;
+                b.flags = (done == 0 && windows_host[w].fresh ? 1 : 0) | (done + b.nb >= nb ? 2 : 0);
+                b.win = w;
+                batches.push_back(b);
+                done += b.nb;
+            } while (done < nb);
+            gbin += nb;
+        }
+    }
+    BinMajorLayout B;      // laid out for the upper bound of the batch count, like the scratch size and the status offset
+    int rc = make_binmajor_layout(n_events, n_windows, TB, H, W, (int)batches_upper_bound(n_windows, TB), B);
+    if (rc) return rc;
+    if (scratch_bytes < B.total) return EVREP_ERR_SCRATCH;
+    const Layout& L = B.L;
+    L_out = L;
+    std::vector<unsigned char> meta((size_t)L.meta_bytes, 0);
+    int64_t* hb = reinterpret_cast<int64_t*>(meta.data() + L.o_wbegin);
+    int64_t* he = reinterpret_cast<int64_t*>(meta.data() + L.o_wend);
+    int64_t* hs = reinterpret_cast<int64_t*>(meta.data() + L.o_wstart);
+    int32_t* hn = reinterpret_cast<int32_t*>(meta.data() + L.o_wnbins);
+    int32_t* hbb = reinterpret_cast<int32_t*>(meta.data() + L.o_wbinbase);
+    int32_t base = 0;
+    for (int w = 0; w < n_windows; ++w) {
+        hb[w] = windows_host[w].ev_begin; he[w] = windows_host[w].ev_end; hs[w] = windows_host[w].start_time;
+        hn[w] = windows_host[w].n_bins; hbb[w] = base;
+        base += windows_host[w].n_bins;
+    }
+    hbb[n_windows] = base;
+    memcpy(meta.data() + L.o_batches, batches.data(), batches.size() * sizeof(Batch));
+    char* s = reinterpret_cast<char*>(scratch);
+    rc = upload_words(reinterpret_cast<const uint32_t*>(meta.data()), L.meta_bytes / 4, reinterpret_cast<uint32_t*>(s), st);
+    if (rc) return rc;
+
+    pl.w_begin = reinterpret_cast<const int64_t*>(s + L.o_wbegin);
+    pl.w_end = reinterpret_cast<const int64_t*>(s + L.o_wend);
+    pl.w_start = reinterpret_cast<const int64_t*>(s + L.o_wstart);
+    pl.w_nbins = reinterpret_cast<const int32_t*>(s + L.o_wnbins);
+    pl.w_binbase = reinterpret_cast<const int32_t*>(s + L.o_wbinbase);
+    pl.batches = reinterpret_cast<const Batch*>(s + L.o_batches);
+    pl.counts = reinterpret_cast<uint32_t*>(s + L.o_counts);
+    pl.bin_any = reinterpret_cast<uint32_t*>(s + L.o_binany);
+    pl.off_rel = reinterpret_cast<uint32_t*>(s + L.o_offrel);
+    pl.tile_total = reinterpret_cast<uint32_t*>(s + L.o_tiletotal);
+    pl.tile_base = reinterpret_cast<uint32_t*>(s + L.o_tilebase);
+    pl.records = reinterpret_cast<uint32_t*>(s + L.o_records);
+    pl.tile_bits = reinterpret_cast<uint32_t*>(s + L.o_tilebits);
+    pl.saved_rec = nullptr; pl.saved_key = nullptr;
+    pl.n_windows = n_windows; pl.n_batches = (int)batches.size(); pl.TB = (int)TB;
+    pl.n_tiles = L.n_tiles; pl.P = L.P; pl.H = H; pl.W = W;
+    pl.div_abin = FastDiv::make((uint32_t)abin);
+    pl.div_P = FastDiv::make((uint32_t)L.P);
+    pl.tile_mul = 0; pl.abin = (uint32_t)abin;
+    src_out = reinterpret_cast<const uint32_t*>(s + B.o_src);
+    status_out = reinterpret_cast<uint32_t*>(s + B.o_status);
+
+    if (TB == 0) {
+        EVREP_CUDA(cudaMemsetAsync(s + L.o_tiletotal, 0, (size_t)(L.o_origins - L.o_tiletotal), st));   // totals, bases, tile bits
+        EVREP_CUDA(cudaMemsetAsync(s + B.o_status, 0, 16, st));
+        return EVREP_OK;
+    }
+    EVREP_CUDA(cudaMemsetAsync(s + L.o_counts, 0, (size_t)(L.o_offrel - L.o_counts), st));   // counts + bin_any
+    EVREP_CUDA(cudaMemsetAsync(s + B.o_bindone, 0, (size_t)(4 * TB), st));
+    SlicePlan sp;
+    sp.status = status_out;
+    sp.w_begin = pl.w_begin; sp.w_end = pl.w_end; sp.w_start = pl.w_start; sp.w_nbins = pl.w_nbins; sp.w_binbase = pl.w_binbase;
+    sp.w_fresh = nullptr;
+    sp.bins = reinterpret_cast<BinDesc*>(s + B.o_bins);
+    sp.slice_bin = reinterpret_cast<uint32_t*>(s + B.o_slicebin);
+    sp.runs = nullptr; sp.records = nullptr;
+    sp.n_windows = n_windows; sp.TB = (int)TB; sp.n_tiles = L.n_tiles; sp.P = L.P; sp.H = H; sp.W = W;
+    sp.pitch = 0; sp.slice_stride = 0; sp.max_slices = (int)B.max_slices;
+    sp.abin = (uint32_t)abin;
+    sp.div_P = pl.div_P;
+    {
+        const uint64_t mul = (1ull << 32) / (uint64_t)L.P + 1;
+        const uint64_t err = mul * (uint64_t)L.P - (1ull << 32);
+        sp.tile_mul = (mul < (1ull << 32) && (uint64_t)H * W * err < (1ull << 32)) ? (uint32_t)mul : 0u;
+    }
+    BinMajorOut bm;
+    bm.cnt16 = reinterpret_cast<uint16_t*>(s + B.o_cnt16);
+    bm.bin_done = reinterpret_cast<uint32_t*>(s + B.o_bindone);
+    bm.counts = pl.counts; bm.src = reinterpret_cast<uint32_t*>(s + B.o_src); bm.bin_any = pl.bin_any; bm.records = pl.records;
+    bm.pitch16 = B.pitch16; bm.TB = (int)TB;
+    SoA ev{t, x, y, p, xmap, ymap};
+    rc = run_slice_front(ev, sp, n_events, sensor_h, sensor_w, &bm, st);
+    if (rc) return rc;
+    taf_scan_rows_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
+    EVREP_LAUNCH_CHECK();
+    taf_scan_tiles_kernel<<<1, 1024, 0, st>>>(pl);
+    EVREP_LAUNCH_CHECK();
+    taf_tile_bits_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
+    EVREP_LAUNCH_CHECK();
     return EVREP_OK;
 }
 

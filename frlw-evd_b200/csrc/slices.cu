@@ -20,7 +20,7 @@ __device__ __forceinline__ uint32_t lower_bound_time(const uint32_t* __restrict_
 __global__ void __launch_bounds__(128)
 slice_bins_kernel(const uint32_t* __restrict__ t, SlicePlan sp) {
     const int gbin = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gbin == 0 && threadIdx.x == 0) { sp.status[0] = 0u; sp.status[1] = 0u; }
+    if (gbin == 0 && threadIdx.x == 0) { sp.status[0] = 0u; sp.status[1] = 0u; sp.status[2] = 0u; sp.status[3] = 0u; }
     if (gbin >= sp.TB) return;
     // window of the bin: the last w with binbase[w] <= gbin (windows without bins share their base with the next one)
     int lo = 0, hi = sp.n_windows;
@@ -47,36 +47,41 @@ slice_bins_kernel(const uint32_t* __restrict__ t, SlicePlan sp) {
     sp.bins[gbin] = bd;
 }
 
-// One CTA: exclusive scan of the bins' slice counts, then the slices' bin indices.
+// One CTA: exclusive scan of the bins' slice counts (and of their record capacities: events + 4 per tile of padding,
+// the bin's region in the bin-major layout), then the slices' bin indices.
 __global__ void __launch_bounds__(1024)
 slice_layout_kernel(SlicePlan sp) {
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t s_carry;
+    __shared__ uint32_t warp_sum[32], warp_cap[32];
+    __shared__ uint32_t s_carry, s_carry_cap;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x == 0) { s_carry = 0; s_carry_cap = 0; }
     __syncthreads();
     for (int base = 0; base < sp.TB; base += 1024) {
         const int b = base + threadIdx.x;
-        uint32_t parts = 0;
-        if (b < sp.TB) parts = slice_parts(sp.bins[b].lo, sp.bins[b].hi);
-        uint32_t incl = parts;
+        uint32_t parts = 0, cap = 0;
+        if (b < sp.TB) {
+            parts = slice_parts(sp.bins[b].lo, sp.bins[b].hi);
+            cap = parts ? ((sp.bins[b].hi - sp.bins[b].lo + 3u) & ~3u) + 4u * (uint32_t)sp.n_tiles : 0u;   // a multiple of 4 records
+        }
+        uint32_t incl = parts, incl_cap = cap;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += v;
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o), c = __shfl_up_sync(0xFFFFFFFFu, incl_cap, o);
+            if (lane >= o) { incl += v; incl_cap += c; }
         }
-        if (lane == 31) warp_sum[wid] = incl;
+        if (lane == 31) { warp_sum[wid] = incl; warp_cap[wid] = incl_cap; }
         __syncthreads();
-        uint32_t before = s_carry;
-        for (int k = 0; k < wid; ++k) before += warp_sum[k];
+        uint32_t before = s_carry, before_cap = s_carry_cap;
+        for (int k = 0; k < wid; ++k) { before += warp_sum[k]; before_cap += warp_cap[k]; }
         const uint32_t first = before + incl - parts;
         if (b < sp.TB) {
             sp.bins[b].first_slice = first;
+            sp.bins[b].win = before_cap + incl_cap - cap;      // first record of the bin's region (bin-major layout)
             for (uint32_t j = 0; j < parts; ++j)
                 if (first + j < (uint32_t)sp.max_slices) sp.slice_bin[first + j] = (uint32_t)b;
         }
         __syncthreads();
-        if (threadIdx.x == 1023) s_carry = before + incl;
+        if (threadIdx.x == 1023) { s_carry = before + incl; s_carry_cap = before_cap + incl_cap; }
         __syncthreads();
     }
     if (threadIdx.x == 0) sp.status[1] = s_carry < (uint32_t)sp.max_slices ? s_carry : (uint32_t)sp.max_slices;
@@ -99,8 +104,14 @@ struct SortSmem {
 // Persistent CTAs, one slice at a time: load (vectorised), classify (coordinate tables in shared
 // memory, tile by one multiply-high), rank inside the tile's run with a returning shared-memory
 // atomic, scan the tile histogram (runs padded to 4 records), place the records, TMA bulk store.
+// kBinMajor: instead of one bulk store per slice, the CTAs that sort the slices of one bin exchange their tile counts
+// (a few KB through L2; a spin on the bin's counter -- every slice of a bin sits in a different resident CTA) and every
+// CTA writes its part of each (bin, tile) run where it belongs: all records of a tile in a bin end up contiguous, the
+// layout the register-resident TAF tile kernel (taf_tile.cu) streams with one copy per chunk.  Records then carry
+// [ d:18 | 2 * local pixel + p ] like the two-pass bucketing's.
+template <bool kBinMajor>
 __global__ void __launch_bounds__(kSortThreads, 2)
-slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, int vec_ok) {
+slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, int vec_ok, BinMajorOut bm) {
     extern __shared__ __align__(128) unsigned char ssm[];
     const SortSmem lay(lut_w, lut_h, sp.n_tiles);
     uint32_t* s_col = reinterpret_cast<uint32_t*>(ssm + lay.lutx);
@@ -147,7 +158,7 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
         __syncthreads();
         for (int i = threadIdx.x; i <= n_tiles; i += kSortThreads) hist[i] = 0;
         if (threadIdx.x == 0) s_flags = 0;
-        {   // padding: every slot a run does not fill holds the null record
+        if (!kBinMajor) {   // padding: every slot a run does not fill holds the null record
             uint4* s4 = reinterpret_cast<uint4*>(sorted);
             const int n4 = (kSliceCap + 4 * n_tiles) / 4;
             for (int i = threadIdx.x; i < n4; i += kSortThreads) s4[i] = make_uint4(kNullRecord, kNullRecord, kNullRecord, kNullRecord);
@@ -234,7 +245,7 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
             d = min(d, kDMax);
             big |= d > kPackedDMax ? 1u : 0u;
             const uint32_t tile = tile_mul ? __umulhi(pix, tile_mul) : sp.div_P.div(pix);
-            rec[k] = (d << 14) | (pol * P + (pix - tile * P));
+            rec[k] = kBinMajor ? (d << 14) | ((pix - tile * P) << 1) | pol : (d << 14) | (pol * P + (pix - tile * P));
             slot[k] = (tile << 14) | atomicAdd(&hist[tile], 1u);
         }
         if (strays) atomicAdd(sp.status, strays);
@@ -247,7 +258,7 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
             const int per = (n_tiles + kSortThreads - 1) / kSortThreads;
             const int b0 = threadIdx.x * per, b1 = min(b0 + per, n_tiles);
             uint32_t mine = 0, raw = 0;
-            for (int i = b0; i < b1; ++i) { const uint32_t c = hist[i]; raw += c; mine += (c + 3u) & ~3u; }
+            for (int i = b0; i < b1; ++i) { const uint32_t c = hist[i]; raw += c; mine += kBinMajor ? c : (c + 3u) & ~3u; }
             uint32_t incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -270,29 +281,110 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
             }
             __syncthreads();
             uint32_t run = s_tmp[wid] + incl - mine;
-            for (int i = b0; i < b1; ++i) { off[i] = run; run += (hist[i] + 3u) & ~3u; }
+            for (int i = b0; i < b1; ++i) { off[i] = run; run += kBinMajor ? hist[i] : (hist[i] + 3u) & ~3u; }
             if (threadIdx.x == kSortThreads - 1 || b1 == n_tiles) off[n_tiles] = s_tmp[kSortThreads / 32];
             n_valid = hist[n_tiles];
             __syncthreads();
         }
-        const uint32_t total = off[n_tiles];               // padded records of the slice
-        // the run table is tile-major: a tile kernel streams its row; neighbouring slices fill the same sectors in L2
-        for (int i = threadIdx.x; i < n_tiles; i += kSortThreads)
-            sp.runs[(int64_t)i * sp.pitch + s] = (off[i] >> 2) | ((off[i + 1] >> 2) << 16);
+        const uint32_t total = off[n_tiles];               // (padded) records of the slice
+        if (!kBinMajor) {
+            // the run table is tile-major: a tile kernel streams its row; neighbouring slices fill the same sectors in L2
+            for (int i = threadIdx.x; i < n_tiles; i += kSortThreads)
+                sp.runs[(int64_t)i * sp.pitch + s] = (off[i] >> 2) | ((off[i + 1] >> 2) << 16);
 #pragma unroll
-        for (int k = 0; k < kSortPerThread; ++k)
-            if (slot[k] != kNone) sorted[off[slot[k] >> 14] + (slot[k] & 0x3FFFu)] = rec[k];
-        fence_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (total) {
-                bulk_store_1d(sp.records + (int64_t)s * sp.slice_stride, sorted, total * 4u);
-                bulk_commit();
+            for (int k = 0; k < kSortPerThread; ++k)
+                if (slot[k] != kNone) sorted[off[slot[k] >> 14] + (slot[k] & 0x3FFFu)] = rec[k];
+            fence_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (total) {
+                    bulk_store_1d(sp.records + (int64_t)s * sp.slice_stride, sorted, total * 4u);
+                    bulk_commit();
+                }
+                const uint32_t dyn = (n_valid ? kBinAny : 0u) | (s_flags ? kBinBigD : 0u);
+                if (dyn) atomicOr(&sp.bins[gbin].dyn, dyn);
             }
-            const uint32_t dyn = (n_valid ? kBinAny : 0u) | (s_flags ? kBinBigD : 0u);
-            if (dyn) atomicOr(&sp.bins[gbin].dyn, dyn);
+            store_pending = true;
+        } else {
+            // (1) publish this slice's tile counts, then wait until every slice of the bin has
+            const uint32_t parts = slice_parts(bd.lo, bd.hi);
+            uint16_t* my_cnt = bm.cnt16 + (int64_t)s * bm.pitch16;
+            for (int i = threadIdx.x; i < n_tiles; i += kSortThreads) my_cnt[i] = (uint16_t)hist[i];
+#pragma unroll
+            for (int k = 0; k < kSortPerThread; ++k)
+                if (slot[k] != kNone) sorted[off[slot[k] >> 14] + (slot[k] & 0x3FFFu)] = rec[k];
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                atomicAdd(bm.bin_done + gbin, 1u);
+                // bounded: a CTA that is never scheduled next to its siblings must not hang the GPU
+                uint32_t polls = 0;
+                while (*reinterpret_cast<volatile uint32_t*>(bm.bin_done + gbin) < parts && ++polls < (1u << 24)) __nanosleep(64);
+                if (polls >= (1u << 24)) atomicAdd(sp.status + 2, 1u);
+                __threadfence();
+            }
+            __syncthreads();
+            // (2) per tile: records of the whole bin (every slice) and of the slices before this one
+            uint32_t* x_prev = sorted + kSliceCap;         // the pad area of the slice layout (4 * n_tiles words) is free here
+            uint32_t* x_tot = x_prev + n_tiles;
+            uint32_t* x_dest = x_tot + n_tiles;
+            for (int i = threadIdx.x; i < n_tiles; i += kSortThreads) {
+                const uint16_t* col = bm.cnt16 + (int64_t)bd.first_slice * bm.pitch16 + i;
+                uint32_t all = 0, prev = 0;
+                for (uint32_t j = 0; j < parts; ++j) {
+                    const uint32_t c = __ldcg(col + (int64_t)j * bm.pitch16);
+                    all += c;
+                    prev += j < part ? c : 0u;
+                }
+                x_prev[i] = prev;
+                x_tot[i] = all;
+            }
+            __syncthreads();
+            // (3) exclusive scan over the tiles of the bin's run lengths, each rounded up to 4 records
+            {
+                const int per = (n_tiles + kSortThreads - 1) / kSortThreads;
+                const int b0 = threadIdx.x * per, b1 = min(b0 + per, n_tiles);
+                uint32_t mine = 0;
+                for (int i = b0; i < b1; ++i) mine += (x_tot[i] + 3u) & ~3u;
+                uint32_t incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (lane == 31) s_tmp[wid] = incl;
+                __syncthreads();
+                if (wid == 0) {
+                    uint32_t w = lane < kSortThreads / 32 ? s_tmp[lane] : 0u, wi = w;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                        if (lane >= o) wi += v;
+                    }
+                    if (lane < kSortThreads / 32) s_tmp[lane] = wi - w;
+                    if (lane == kSortThreads / 32 - 1) s_tmp[kSortThreads / 32] = wi;
+                }
+                __syncthreads();
+                uint32_t run = bd.win + s_tmp[wid] + incl - mine;       // bd.win = first record of the bin's region
+                for (int i = b0; i < b1; ++i) {
+                    const uint32_t padded = (x_tot[i] + 3u) & ~3u;
+                    if (part == 0u) {                       // the bin's first slice writes the bin's tables and the padding
+                        bm.counts[(int64_t)i * bm.TB + gbin] = padded;
+                        bm.src[(int64_t)i * bm.TB + gbin] = run;
+                        for (uint32_t q = x_tot[i]; q < padded; ++q) bm.records[run + q] = kNullRecord;
+                    }
+                    x_dest[i] = run + x_prev[i];
+                    run += padded;
+                }
+                if (threadIdx.x == 0 && part == 0u) bm.bin_any[gbin] = s_tmp[kSortThreads / 32] ? 1u : 0u;
+                __syncthreads();
+            }
+            // (4) every warp copies whole runs: sorted[local offset ...] -> records[destination ...]
+            for (int i = wid; i < n_tiles; i += kSortThreads / 32) {
+                const uint32_t cnt = hist[i], from = off[i], to = x_dest[i];
+                for (uint32_t q = lane; q < cnt; q += 32u) bm.records[to + q] = sorted[from + q];
+            }
         }
-        store_pending = true;
         gbin = gbin_next; bd = bd_next;
     }
     if (store_pending && threadIdx.x == 0) bulk_wait_all();
@@ -417,26 +509,36 @@ int prepare_slices(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
         sp.tile_mul = (mul < (1ull << 32) && (uint64_t)H * W * err < (1ull << 32)) ? (uint32_t)mul : 0u;
     }
 
+    SoA ev{t, x, y, p, xmap, ymap};
+    return run_slice_front(ev, sp, n_events, sensor_h, sensor_w, nullptr, st);
+}
+
+int run_slice_front(const SoA& ev, const SlicePlan& sp, int64_t n_events, int sensor_h, int sensor_w, const BinMajorOut* bm,
+                    cudaStream_t st) {
     // status words are reset by the bins kernel; with no bins at all there is nothing to sort
-    if (TB == 0) {
-        EVREP_CUDA(cudaMemsetAsync(s + L.o_status, 0, 16, st));
+    if (sp.TB == 0) {
+        EVREP_CUDA(cudaMemsetAsync(sp.status, 0, 16, st));
         return EVREP_OK;
     }
-    slice_bins_kernel<<<(int)((TB + 127) / 128), 128, 0, st>>>(t, sp);
+    slice_bins_kernel<<<(sp.TB + 127) / 128, 128, 0, st>>>(ev.t, sp);
     EVREP_LAUNCH_CHECK();
     slice_layout_kernel<<<1, 1024, 0, st>>>(sp);
     EVREP_LAUNCH_CHECK();
-    const bool use_lut = xmap && ymap;
-    const int lut_w = use_lut ? sensor_w : W, lut_h = use_lut ? sensor_h : H;
-    const size_t smem = (size_t)SortSmem(lut_w, lut_h, n_tiles).total;
+    const bool use_lut = ev.xmap && ev.ymap;
+    const int lut_w = use_lut ? sensor_w : sp.W, lut_h = use_lut ? sensor_h : sp.H;
+    const size_t smem = (size_t)SortSmem(lut_w, lut_h, sp.n_tiles).total;
     if (smem > 110 * 1024) return EVREP_ERR_RANGE;                        // two CTAs per SM
-    const int vec_ok = !((reinterpret_cast<uintptr_t>(t) & 15) | (reinterpret_cast<uintptr_t>(x) & 7) |
-                         (reinterpret_cast<uintptr_t>(y) & 7) | (reinterpret_cast<uintptr_t>(p) & 3));
+    const int vec_ok = !((reinterpret_cast<uintptr_t>(ev.t) & 15) | (reinterpret_cast<uintptr_t>(ev.x) & 7) |
+                         (reinterpret_cast<uintptr_t>(ev.y) & 7) | (reinterpret_cast<uintptr_t>(ev.p) & 3));
     const int64_t resident = 2ll * sm_count();
-    const int grid = (int)(L.max_slices < resident ? L.max_slices : resident);
-    SoA ev{t, x, y, p, xmap, ymap};
-    EVREP_CUDA(cudaFuncSetAttribute(slice_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    slice_sort_kernel<<<grid, kSortThreads, smem, st>>>(ev, sp, n_events, lut_w, lut_h, vec_ok);
+    const int grid = (int)(sp.max_slices < resident ? sp.max_slices : resident);
+    if (bm) {
+        EVREP_CUDA(cudaFuncSetAttribute(slice_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        slice_sort_kernel<true><<<grid, kSortThreads, smem, st>>>(ev, sp, n_events, lut_w, lut_h, vec_ok, *bm);
+    } else {
+        EVREP_CUDA(cudaFuncSetAttribute(slice_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        slice_sort_kernel<false><<<grid, kSortThreads, smem, st>>>(ev, sp, n_events, lut_w, lut_h, vec_ok, BinMajorOut{});
+    }
     EVREP_LAUNCH_CHECK();
     return EVREP_OK;
 }

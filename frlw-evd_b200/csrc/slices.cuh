@@ -39,7 +39,7 @@ struct BinDesc {                 // 32 bytes, one per global bin
     uint32_t first_slice;        // slices first_slice .. first_slice + ceil((hi - lo) / kSliceMax) - 1
     uint32_t flags;              // kBinFirst | kBinLast
     uint32_t dyn;                // kBinAny | kBinBigD, OR-ed in by the sort CTAs
-    uint32_t win;
+    uint32_t win;                // after slice_layout_kernel: first record of the bin's region in the bin-major layout
 };
 static_assert(sizeof(BinDesc) == 32, "BinDesc layout");
 
@@ -88,6 +88,22 @@ int prepare_slices(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
                    const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W, int P, int n_tiles,
                    const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
                    void* scratch, int64_t scratch_bytes, cudaStream_t st, SlicePlan& sp, SliceLayout& L);
+
+// Output of the sort's bin-major mode (see slice_sort_kernel): what the register-resident TAF tile kernel reads.
+struct BinMajorOut {
+    uint16_t* cnt16;         // [max_slices][pitch16] tile counts of every slice
+    uint32_t* bin_done;      // [TB] slices of the bin that have published their counts (zero on entry)
+    uint32_t* counts;        // [n_tiles][TB] padded run length of (tile, bin): input of taf_scan_rows_kernel (zero on entry)
+    uint32_t* src;           // [n_tiles][TB] first record of the (tile, bin) run in `records`
+    uint32_t* bin_any;       // [TB] (zero on entry)
+    uint32_t* records;
+    int pitch16, TB;
+};
+constexpr int kBinMajorMaxParts = 128;             // slices a bin may have in that mode: they must all be resident at once
+
+// Bins by bisection, slice layout, the sort (slices, or bin-major when `bm` is given), on `st`.
+int run_slice_front(const SoA& ev, const SlicePlan& sp, int64_t n_events, int sensor_h, int sensor_w, const BinMajorOut* bm,
+                    cudaStream_t st);
 
 // ---- record feed of the tile kernels ------------------------------------------------------------
 // The producer warps of a CTA walk the windows and bins of the plan (all of them the same way), gather the

@@ -260,4 +260,13 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
                    void* scratch, int64_t scratch_bytes, cudaStream_t st, StreamPlan& pl, Layout& L,
                    int tiles_per_sm = 1);
 
+// Time-ordered input: one-pass bin-major sort in front of the same tile kernels (bucketing.cu).
+int64_t binmajor_scratch_bytes(int64_t n_events, int n_windows, int64_t TB, int H, int W);
+int64_t binmajor_status_offset(int64_t n_events, int n_windows, int64_t TB, int H, int W);
+int prepare_stream_binmajor(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+                            const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W,
+                            const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                            void* scratch, int64_t scratch_bytes, cudaStream_t st, StreamPlan& pl, Layout& L,
+                            const uint32_t*& src, uint32_t*& status);
+
 }  // namespace evrep

@@ -495,7 +495,7 @@ using namespace evrep;
 
 extern "C" {
 
-int64_t evrep_taf_stream_ordered_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins, int H, int W, int K) {
+int64_t evrep_taf_stream_sliced_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins, int H, int W, int K) {
     if (n_events < 0 || n_windows < 0 || total_bins < 0 || H <= 0 || W <= 0 || (K != 4 && K != 8)) return EVREP_ERR_ARG;
     int P, n_tiles;
     int rc = choose_tile(H, W, K, taf_slice_smem, taf_ordered_ctas_per_sm(), P, n_tiles);
@@ -506,7 +506,7 @@ int64_t evrep_taf_stream_ordered_scratch_bytes(int64_t n_events, int n_windows, 
     return L.total;
 }
 
-int evrep_taf_stream_ordered(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+int evrep_taf_stream_sliced(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
                              const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W, int K,
                              const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
                              float* state_inout, int emit_state_every_window,

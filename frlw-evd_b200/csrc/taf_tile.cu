@@ -28,6 +28,7 @@ struct TileParams {
     int n_emits;           // number of windows (batches that end a window)
     int bulk_out;          // out rows are 16-byte aligned: emit through smem + TMA bulk stores
     float span;            // f32(abin + 1e-8)
+    const uint32_t* src;   // bin-major records (kRuns kernels): first record of the (tile, bin) run, [n_tiles][TB]
 };
 
 // Shared-memory carve-up of the tile kernel (all offsets multiples of 128 bytes).
@@ -303,7 +304,11 @@ taf_tile_kernel(TileParams tp) {
 // Hand-over uses named barriers (bar.arrive / bar.sync): FULL[buf] accumulate -> consumers,
 // EMPTY[buf] consumers -> accumulate, STAGED consumers -> store warp, STAGE_FREE store warp ->
 // consumers.  4 warps per SM sub-partition: 1 producer-group warp + 3 consumers.
-template <int K, int SLOTS>
+// kRuns: the records are laid out bin-major (slices.cu, bin-major sort): a tile's list is the concatenation of its
+// per-bin runs, each padded to 16 bytes with null records, and lives at src[tile][bin] instead of one contiguous
+// range.  The ring, the offsets (off_rel counts the padded records) and the roles are the same; a 2 KB chunk of the
+// list is fetched with one bulk copy per run it touches (one or two).
+template <int K, int SLOTS, bool kRuns>
 __global__ void __launch_bounds__(kWsThreads, 1)
 taf_tile_ws_kernel(TileParams tp) {
     const StreamPlan& pl = tp.pl;
@@ -353,15 +358,40 @@ taf_tile_ws_kernel(TileParams tp) {
             return;
         }
         // ================================ accumulate warps ================================
-        const uint32_t* my_records = pl.records + pl.tile_base[tile];
+        const uint32_t* my_records = kRuns ? pl.records : pl.records + pl.tile_base[tile];
         const uint32_t list_len = (pl.tile_total[tile] + 3u) & ~3u;
         const int n_chunks = (int)((list_len + kWsChunkRecords - 1) / kWsChunkRecords);
-        auto issue = [&](int c) {           // thread 0 only
+        // kRuns, thread 0: cursor over the tile's runs -- bin `ib` holds list positions [v_lo, v_hi) at record src_ib;
+        // the next bin's end and source are fetched one bin ahead
+        const uint32_t* my_src = kRuns ? tp.src + (int64_t)tile * pl.TB : nullptr;
+        int ib = 0;
+        uint32_t v_lo = 0, v_hi = 0, src_ib = 0, v_hi_next = 0, src_next = 0;
+        if (kRuns && tid == 0 && pl.TB > 0) {
+            v_hi = my_off[1]; src_ib = my_src[0];
+            if (pl.TB > 1) { v_hi_next = my_off[2]; src_next = my_src[1]; }
+        }
+        auto issue = [&](int c) {           // thread 0 only; chunks are requested in increasing order
             const uint32_t first = (uint32_t)c * kWsChunkRecords;
             const uint32_t bytes = min((uint32_t)kWsChunkRecords, list_len - first) * 4u;
             uint64_t* bar = full + (c % kWsStages);
             mbar_expect_tx(bar, bytes);
-            tma_load_1d(ring + (c % kWsStages) * kWsChunkRecords, my_records + first, bytes, bar);
+            if (!kRuns) {
+                tma_load_1d(ring + (c % kWsStages) * kWsChunkRecords, my_records + first, bytes, bar);
+                return;
+            }
+            uint32_t cur = first;
+            const uint32_t end = first + bytes / 4u;
+            while (cur < end) {
+                while (v_hi <= cur) {               // the run of bin ib is used up (or empty): on to the next bin
+                    ++ib;
+                    v_lo = v_hi; v_hi = v_hi_next; src_ib = src_next;
+                    if (ib + 1 < pl.TB) { v_hi_next = __ldg(my_off + ib + 2); src_next = __ldg(my_src + ib + 1); }
+                }
+                const uint32_t piece_end = v_hi < end ? v_hi : end;
+                tma_load_1d(ring + (c % kWsStages) * kWsChunkRecords + (cur - first), my_records + src_ib + (cur - v_lo),
+                            (piece_end - cur) * 4u, bar);
+                cur = piece_end;
+            }
         };
         if (tid == 0)
             for (int c = 0; c < n_chunks && c < kWsStages; ++c) issue(c);
@@ -441,6 +471,7 @@ taf_tile_ws_kernel(TileParams tp) {
                     }
                     for (uint32_t r = o0 + tid + kPre * kAccumThreads; r < o1; r += kAccumThreads) {
                         const uint32_t rec = ring[r & (kWsRing - 1)];
+                        if (kRuns && rec == kNoRec) continue;           // run padding
                         uint2* cell = my_acc + (rec & 0x3FFFu);
                         atomicAdd(&cell->x, 1u);
                         atomicAdd(&cell->y, rec >> 14);
@@ -465,6 +496,7 @@ taf_tile_ws_kernel(TileParams tp) {
                         }
                         for (uint32_t r = cur + tid; r < seg_end; r += kAccumThreads) {
                             const uint32_t rec = ring[r & (kWsRing - 1)];
+                            if (kRuns && rec == 0xFFFFFFFFu) continue;      // run padding
                             uint2* cell = my_acc + (rec & 0x3FFFu);
                             atomicAdd(&cell->x, 1u);
                             atomicAdd(&cell->y, rec >> 14);
@@ -631,14 +663,14 @@ taf_tile_ws_kernel(TileParams tp) {
     }
 }
 
-template <int K>
+template <int K, bool kRuns>
 static int launch_tiles_ws(const TileParams& tp, cudaStream_t st) {
     const int slots = (tp.pl.P + kConsumerThreads - 1) / kConsumerThreads;
     const size_t smem = (size_t)TileSmemWS(tp.pl.P, K).total;
 #define EVREP_TILE_WS(S)                                                                                  \
     case S:                                                                                               \
-        EVREP_CUDA(cudaFuncSetAttribute(taf_tile_ws_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        taf_tile_ws_kernel<K, S><<<tp.pl.n_tiles, kWsThreads, smem, st>>>(tp);                            \
+        EVREP_CUDA(cudaFuncSetAttribute(taf_tile_ws_kernel<K, S, kRuns>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        taf_tile_ws_kernel<K, S, kRuns><<<tp.pl.n_tiles, kWsThreads, smem, st>>>(tp);                     \
         break;
     switch (slots) {
         EVREP_TILE_WS(1) EVREP_TILE_WS(2) EVREP_TILE_WS(3) EVREP_TILE_WS(4) EVREP_TILE_WS(5) EVREP_TILE_WS(6)
@@ -702,13 +734,58 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
     tp.n_emits = n_windows;
     tp.span = (float)((double)abin + 1e-8);
     tp.bulk_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    tp.src = nullptr;
 
     const size_t smem = (size_t)TileSmem(L.P, K).total;
     if (ev_tiles_begin) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_begin), st));
     const char* legacy = getenv("EVREP_TAF_TILE_KERNEL");            // "single" = the non-specialised kernel (A/B runs)
     const bool ws = !(legacy && strcmp(legacy, "single") == 0) && (size_t)TileSmemWS(L.P, K).total <= 232448;
-    if (ws) rc = K == 8 ? launch_tiles_ws<8>(tp, st) : launch_tiles_ws<4>(tp, st);
+    if (ws) rc = K == 8 ? launch_tiles_ws<8, false>(tp, st) : launch_tiles_ws<4, false>(tp, st);
     else rc = K == 8 ? launch_tiles<8>(tp, L.slots, smem, st) : launch_tiles<4>(tp, L.slots, smem, st);
+    if (rc) return rc;
+    if (ev_tiles_end) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_end), st));
+    return EVREP_OK;
+}
+
+
+int64_t evrep_taf_stream_ordered_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins, int H, int W) {
+    if (n_events < 0 || n_windows < 0 || total_bins < 0 || H <= 0 || W <= 0) return EVREP_ERR_ARG;
+    return binmajor_scratch_bytes(n_events, n_windows, total_bins, H, W);
+}
+
+int64_t evrep_taf_stream_ordered_status_offset(int64_t n_events, int n_windows, int64_t total_bins, int H, int W) {
+    if (n_events < 0 || n_windows < 0 || total_bins < 0 || H <= 0 || W <= 0) return EVREP_ERR_ARG;
+    return binmajor_status_offset(n_events, n_windows, total_bins, H, W);
+}
+
+int evrep_taf_stream_ordered(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p, int64_t n_events,
+                             const evrep_taf_window* windows_host, int n_windows, int abin, int H, int W, int K,
+                             const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                             float* state_inout, int emit_state_every_window,
+                             float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
+                             void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream) {
+    if (n_events < 0 || n_windows < 0 || H <= 0 || W <= 0 || abin <= 0 || !state_inout || !scratch) return EVREP_ERR_ARG;
+    if (K != 4 && K != 8) return EVREP_ERR_ARG;
+    if (n_windows == 0) return EVREP_OK;
+    if (!out || (reinterpret_cast<uintptr_t>(state_inout) & 15)) return EVREP_ERR_ARG;
+    cudaStream_t st = as_stream(stream);
+    StreamPlan pl;
+    Layout L;
+    const uint32_t* src = nullptr;
+    uint32_t* status = nullptr;
+    int rc = prepare_stream_binmajor(t, x, y, p, n_events, windows_host, n_windows, abin, H, W, xmap, ymap, sensor_h, sensor_w,
+                                     scratch, scratch_bytes, st, pl, L, src, status);
+    if (rc) return rc;
+    if ((size_t)TileSmemWS(L.P, K).total > 232448) return EVREP_ERR_RANGE;
+    TileParams tp;
+    tp.pl = pl; tp.state = state_inout; tp.out = out; tp.out_stride = out_stride;
+    tp.emit_state = emit_state_every_window;
+    tp.n_emits = n_windows;
+    tp.span = (float)((double)abin + 1e-8);
+    tp.bulk_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    tp.src = src;
+    if (ev_tiles_begin) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_begin), st));
+    rc = K == 8 ? launch_tiles_ws<8, true>(tp, st) : launch_tiles_ws<4, true>(tp, st);
     if (rc) return rc;
     if (ev_tiles_end) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_end), st));
     return EVREP_OK;

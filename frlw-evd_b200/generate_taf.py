@@ -155,8 +155,11 @@ class HostPipeline:
         dev = self.device
         self.raw = [torch.empty(max(max_ev, 1) * 8, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.soa = [ops.EventStream.empty(max(max_ev, 1), dev) for _ in range(2)]
-        self.assume_ordered = os.environ.get("EVREP_TAF_PATH", "") == "ordered"
-        self.fused_u8 = self.assume_ordered and tuple(geom.grid) == tuple(geom.target)
+        # a .dat payload is ordered in time (the reference's loader seeks by bisection on that assumption), so the one-pass
+        # kernels may be selected: EVREP_TAF_PATH=ordered (bin-major sort) or =sliced (shared-memory tile kernel, which
+        # writes the file bytes itself when no resize follows).  The default is the general two-pass bucketing.
+        self.assume_ordered = os.environ.get("EVREP_TAF_PATH", "") in ("ordered", "sliced")
+        self.fused_u8 = os.environ.get("EVREP_TAF_PATH", "") == "sliced" and tuple(geom.grid) == tuple(geom.target)
         self.vol = None if self.fused_u8 else torch.empty((max(max_w, 1), 2 * K, H, W), dtype=torch.float32, device=dev)
         self.violations = torch.zeros(1, dtype=torch.int32, device=dev)
         self.ring = None                   # pinned chunk buffers of the `sink` mode, allocated on first use
@@ -219,7 +222,8 @@ class HostPipeline:
                     ops.taf_stream(soa, local, self.abin, self.geom.grid, self.K, self.state, self.geom.coord_maps, False, vol)
                     ops.taf_leaky_u8_batch(vol, self.K, self.geom.target, self.geom.resize_maps, self.u8[k][:b - a])
                 if self.assume_ordered:
-                    self.violations += ops.order_violations_tensor(self.device)
+                    status = ops.order_violations_tensor(self.device)
+                    self.violations += status[0] + status[2]
                 comp_done[k].record(self.s_comp)
             if sink is not None:
                 if c:
@@ -252,8 +256,8 @@ class HostPipeline:
 
     def order_violations(self) -> int:
         """Events found outside the bin their position implies, over all runs so far (synchronises).
-        Only the ``EVREP_TAF_PATH=ordered`` kernels count them; non-zero means the payload was not ordered in
-        time and the run has to be repeated on the default path."""
+        Non-zero means the payload was not ordered in time (or the sort could not run to completion) and the run
+        has to be repeated with ``EVREP_TAF_PATH=bucketed``."""
         return int(self.violations.item())
 
 

@@ -347,20 +347,27 @@ def taf_bin_aos64(events, shape, K: int, state):
     return out, new_state
 
 
+TAF_ORDERED_MAX_WINDOW = 128 * 8188      # events per window the one-pass ordered path accepts (kBinMajorMaxParts slices)
+_last_status = {}                        # device index -> int32 view of the status block of the last ordered TAF call
+
+
 def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=None,
                emit_state_every_window=False, out=None, tile_events=None, out_u8=None, want_f32=True):
     """T2: run a list of windows ``(ev_begin, ev_end, start_time, n_bins, fresh)`` through the
     whole-stream TAF kernels.  ``state`` (f32 ``[H,W,2,K]``) is updated IN PLACE.  Returns f32
     ``[n_windows, 2K, H, W]`` (``None`` with ``want_f32=False``).  ``out_u8``: optional u8
     ``[n_windows, K, 2, H, W]`` filled with the bytes of the ``bins*`` files (leaky transform +
-    slot flip, ``generate_taf.py:226-235``) straight from the tile kernel.  ``tile_events``:
-    optional pair of ``torch.cuda.Event(enable_timing=True)`` recorded around the tile kernel.
+    slot flip, ``generate_taf.py:226-235``).  ``tile_events``: optional pair of
+    ``torch.cuda.Event(enable_timing=True)`` recorded around the tile kernel.
 
-    Two implementations with the same results: the general two-pass bucketing + register-resident
-    tile kernel (``evrep_taf_stream``, the default: the faster one on every BASELINE configuration,
-    see DESIGN.md section 4.1e), and, with ``EVREP_TAF_PATH=ordered`` and a time-ordered stream
-    (``ev.is_ordered()``), the one-pass slice sort + shared-memory tile kernel
-    (``evrep_taf_stream_ordered``), which can also write the uint8 file bytes itself."""
+    Three implementations with the same results:
+    * default (and ``EVREP_TAF_PATH=bucketed``): the general two-pass bucketing (``evrep_taf_stream``), the
+      fastest of the three as measured (DESIGN.md section 8);
+    * ``EVREP_TAF_PATH=ordered``, time-ordered streams (``ev.is_ordered()``) whose windows hold at most
+      ``TAF_ORDERED_MAX_WINDOW`` events: one-pass bin-major sort + register-resident tile kernel
+      (``evrep_taf_stream_ordered``);
+    * ``EVREP_TAF_PATH=sliced``: slice sort + shared-memory tile kernel with lazy ageing
+      (``evrep_taf_stream_sliced``), which writes ``out_u8`` itself."""
     _need_cuda(ev.t, state)
     H, W = shape
     nw = len(windows)
@@ -372,48 +379,61 @@ def taf_stream(ev: EventStream, windows, abin: int, shape, K: int, state, maps=N
     xm, ym = _maps(maps)
     sensor = maps.sensor_shape if maps is not None else (H, W)
     lib = _lib.load()
-    ordered = os.environ.get("EVREP_TAF_PATH", "") == "ordered" and ev.is_ordered()
-    if ordered:
-        need = lib.evrep_taf_stream_ordered_scratch_bytes(ev.n, nw, total_bins, H, W, K)
+    path = os.environ.get("EVREP_TAF_PATH", "")
+    if path == "sliced" and ev.is_ordered():
+        need = lib.evrep_taf_stream_sliced_scratch_bytes(ev.n, nw, total_bins, H, W, K)
         if need < 0:
-            _lib.check(int(need), "evrep_taf_stream_ordered_scratch_bytes")
+            _lib.check(int(need), "evrep_taf_stream_sliced_scratch_bytes")
         buf = workspace("taf_ordered", need, ev.device)
         if out_u8 is not None:
             assert out_u8.is_contiguous() and out_u8.dtype == torch.uint8 and out_u8.numel() >= nw * 2 * K * H * W
-        _call("evrep_taf_stream_ordered", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
-                  arr, nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
-                  int(bool(emit_state_every_window)), _ptr(out), 2 * K * H * W, _ptr(out_u8), 2 * K * H * W,
-                  _ptr(buf), buf.numel(),
-                  _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
+        _call("evrep_taf_stream_sliced", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+              arr, nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
+              int(bool(emit_state_every_window)), _ptr(out), 2 * K * H * W, _ptr(out_u8), 2 * K * H * W,
+              _ptr(buf), buf.numel(),
+              _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
+        _last_status[_dev_index(ev.device)] = buf[:16].view(torch.int32)
         return out
-    need = lib.evrep_taf_stream_scratch_bytes(ev.n, nw, total_bins, H, W)
-    if need < 0:
-        _lib.check(int(need), "evrep_taf_stream_scratch_bytes")
-    buf = workspace("taf_stream", need, ev.device)
     vol = out if out is not None else torch.empty((nw, 2 * K, H, W), dtype=torch.float32, device=ev.device)
-    _call("evrep_taf_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+    small = all(int(w[1]) - int(w[0]) <= TAF_ORDERED_MAX_WINDOW for w in windows)
+    if path == "ordered" and small and ev.is_ordered():
+        need = lib.evrep_taf_stream_ordered_scratch_bytes(ev.n, nw, total_bins, H, W)
+        if need < 0:
+            _lib.check(int(need), "evrep_taf_stream_ordered_scratch_bytes")
+        buf = workspace("taf_ordered", need, ev.device)
+        _call("evrep_taf_stream_ordered", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
               arr, nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
               int(bool(emit_state_every_window)), _ptr(vol), 2 * K * H * W, _ptr(buf), buf.numel(),
               _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
+        at = int(lib.evrep_taf_stream_ordered_status_offset(ev.n, nw, total_bins, H, W))
+        _last_status[_dev_index(ev.device)] = buf[at:at + 16].view(torch.int32)
+    else:
+        need = lib.evrep_taf_stream_scratch_bytes(ev.n, nw, total_bins, H, W)
+        if need < 0:
+            _lib.check(int(need), "evrep_taf_stream_scratch_bytes")
+        buf = workspace("taf_stream", need, ev.device)
+        _call("evrep_taf_stream", _ptr(ev.t), _ptr(ev.x), _ptr(ev.y), _ptr(ev.p), ev.n,
+              arr, nw, int(abin), H, W, K, xm, ym, sensor[0], sensor[1], _ptr(state),
+              int(bool(emit_state_every_window)), _ptr(vol), 2 * K * H * W, _ptr(buf), buf.numel(),
+              _event(tile_events, 0, ev.device), _event(tile_events, 1, ev.device), _stream(ev.device))
+        _last_status.pop(_dev_index(ev.device), None)
     if out_u8 is not None:
         taf_leaky_u8_batch(vol, K, out=out_u8)
     return out
 
 
 def order_violations_tensor(device) -> torch.Tensor:
-    """Device view (int32 ``[1]``) of the order-violation counter of the last ordered ``taf_stream`` call."""
-    return _workspace_peek("taf_ordered", device)[:4].view(torch.int32)
+    """Device view (int32 ``[4]``) of the status block of the last ordered ``taf_stream`` call on ``device``: ``[0]`` events
+    found outside the bin their position implies, ``[2]`` sort CTAs that gave up waiting for their bin's siblings."""
+    view = _last_status.get(_dev_index(device))
+    return view if view is not None else torch.zeros(4, dtype=torch.int32, device=device)
 
 
 def order_violations(device) -> int:
-    """Events the last ``taf_stream`` call on the ordered path found outside the bin their position
-    implies (0 = the stream really was ordered).  Synchronises the current stream."""
-    buf = _workspace_peek("taf_ordered", device)
-    if buf is None:
-        return 0
-    host = ctypes.c_uint32(0)
-    _call("evrep_stream_order_violations", _ptr(buf), ctypes.byref(host), _stream(buf.device))
-    return int(host.value)
+    """Problems the last ``taf_stream`` call on an ordered path reported (0 = the stream really was ordered and the sort
+    ran to completion).  Synchronises."""
+    st = order_violations_tensor(device).cpu()
+    return int(st[0]) + int(st[2])
 
 
 def _event(pair, i, device):

@@ -195,7 +195,28 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
                      void* scratch, int64_t scratch_bytes,
                      void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream);
 
-/* -------------------------- T2 (time-ordered input): Temporal Active Focus, whole streams ------
+/* ------------- T2 (time-ordered input, the fast path): one-pass bin-major sort + the tile kernel of evrep_taf_stream
+ * Same contract and results as evrep_taf_stream for streams whose timestamps are non-decreasing over
+ * [windows[0].ev_begin, windows[n-1].ev_end).  Every bin of a window is then one contiguous index range: the bins'
+ * ranges come from bisection, every bin is cut into slices of <= 8188 events, one CTA sorts a slice by sensor tile in
+ * shared memory, the CTAs of a bin's slices exchange their tile counts and write every (bin, tile) run contiguously
+ * (9 bytes read + 4 written per event, one pass instead of two); the register-resident tile kernel then fetches a
+ * 2 KB chunk of a tile's list with one bulk copy per run it touches.  Windows of more than 128 x 8188 events return
+ * EVREP_ERR_RANGE (use evrep_taf_stream).  Order violations are counted, not repaired: after the call (stream order)
+ * the status block inside `scratch` says how many events lie outside the bin their position implies; pass
+ * scratch + evrep_taf_stream_ordered_status_offset(...) to evrep_stream_order_violations. */
+int64_t evrep_taf_stream_ordered_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins, int H, int W);
+/* byte offset of the status block inside `scratch`: u32 [0] order violations, [2] sort CTAs that gave up waiting */
+int64_t evrep_taf_stream_ordered_status_offset(int64_t n_events, int n_windows, int64_t total_bins, int H, int W);
+int evrep_taf_stream_ordered(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
+                             int64_t n_events, const evrep_taf_window* windows_host, int n_windows,
+                             int abin, int H, int W, int K,
+                             const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
+                             float* state_inout, int emit_state_every_window,
+                             float* out, int64_t out_stride, void* scratch, int64_t scratch_bytes,
+                             void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream);
+
+/* ------------- T2 (time-ordered input, shared-memory variant): slice sort + tile kernel with lazy ageing ------
  * Same contract and results as evrep_taf_stream for streams whose timestamps are non-decreasing
  * over [windows[0].ev_begin, windows[n-1].ev_end) -- what src/io/psee_loader.py hands out, and
  * what generate_taf.py:188-193 assumes when it seeks by time.  Every bin of a window is then one
@@ -213,9 +234,9 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
  * evrep_stream_order_violations copies that word to the host (it synchronises the stream).  With a
  * non-zero count the result is not the reference's: use evrep_taf_stream for unordered input.
  * K must be 4 or 8; abin <= 262143; tiles of at most 4096 pixels. */
-int64_t evrep_taf_stream_ordered_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins,
+int64_t evrep_taf_stream_sliced_scratch_bytes(int64_t n_events, int n_windows, int64_t total_bins,
                                                int H, int W, int K);
-int evrep_taf_stream_ordered(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
+int evrep_taf_stream_sliced(const uint32_t* t, const uint16_t* x, const uint16_t* y, const uint8_t* p,
                              int64_t n_events, const evrep_taf_window* windows_host, int n_windows,
                              int abin, int H, int W, int K,
                              const uint16_t* xmap, const uint16_t* ymap, int sensor_h, int sensor_w,
@@ -257,7 +278,7 @@ int evrep_event_volume_stream(const uint32_t* t, const uint16_t* x, const uint16
  * them with start_time <= t < start_time + 262144 -- and gives every window ("span") as a run of
  * segments first_segment .. last_segment (inclusive; first > last = no events) with its own origin
  * t0 and length tw: t_norm = (t - t0) / tw in float64 (:141).  The events are sorted once by
- * (segment, sensor tile) with the one-pass slice sort of evrep_taf_stream_ordered; every span
+ * (segment, sensor tile) with the one-pass slice sort of evrep_taf_stream_sliced; every span
  * then re-reads the 4-byte records of its segments and splats them with its own normalisation
  * (shared-memory fixed-point accumulators as in evrep_event_volume_stream, one CTA per tile).
  * No limit on tw below 2^31 us.  Timestamps must be non-decreasing over the segments.

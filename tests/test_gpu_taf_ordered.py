@@ -1,5 +1,6 @@
-"""The time-ordered TAF path (slice sort + shared-memory tile kernel, `evrep_taf_stream_ordered`,
-selected with EVREP_TAF_PATH=ordered) against the oracle and against the default two-pass path: hot pixels (exact two-word
+"""The two TAF paths for time-ordered streams -- the default one-pass bin-major sort in front of the register-resident
+tile kernel (`evrep_taf_stream_ordered`) and the slice sort + shared-memory tile kernel (`evrep_taf_stream_sliced`,
+EVREP_TAF_PATH=sliced) -- against the oracle and against the general two-pass path (EVREP_TAF_PATH=bucketed): hot pixels (exact two-word
 accumulators), wide offsets, bins of many slices, the native 1MP grid (several waves of tiles),
 K = 4 under the gen4 policy, the in-kernel uint8 output and the order check.
 Float tolerance 1e-5 rel / 1e-6 abs (BASELINE.json north_star)."""
@@ -24,15 +25,23 @@ def idx(t, v):
     return int(np.searchsorted(t, v))
 
 
-def both_paths(monkeypatch, ev, windows, abin, grid, K, maps=None):
-    """(ordered result, ordered state, bucketed result, bucketed state)."""
-    monkeypatch.setenv("EVREP_TAF_PATH", "ordered")
-    s1 = ops.taf_fresh_state(grid, K, DEV)
-    a = ops.taf_stream(ev, windows, abin, grid, K, s1, maps)
-    assert ops.order_violations(DEV) == 0
+def run_path(monkeypatch, path, ev, windows, abin, grid, K, maps=None):
+    monkeypatch.setenv("EVREP_TAF_PATH", path)
+    state = ops.taf_fresh_state(grid, K, DEV)
+    out = ops.taf_stream(ev, windows, abin, grid, K, state, maps)
+    if path != "bucketed":
+        assert ops.order_violations(DEV) == 0
     monkeypatch.delenv("EVREP_TAF_PATH", raising=False)
-    s2 = ops.taf_fresh_state(grid, K, DEV)
-    b = ops.taf_stream(ev, windows, abin, grid, K, s2, maps)
+    return out, state
+
+
+def both_paths(monkeypatch, ev, windows, abin, grid, K, maps=None):
+    """(sliced result, sliced state, bucketed result, bucketed state); the default ordered path must agree with the
+    bucketed one bit for bit (same tile kernel arithmetic, integer sums)."""
+    a, s1 = run_path(monkeypatch, "sliced", ev, windows, abin, grid, K, maps)
+    b, s2 = run_path(monkeypatch, "bucketed", ev, windows, abin, grid, K, maps)
+    c, s3 = run_path(monkeypatch, "ordered", ev, windows, abin, grid, K, maps)
+    assert torch.equal(b, c) and torch.equal(s2, s3)
     return a, s1, b, s2
 
 
@@ -107,10 +116,10 @@ def test_bin_of_many_slices(monkeypatch):
 
 @pytest.fixture
 def ordered_path(monkeypatch):
-    monkeypatch.setenv("EVREP_TAF_PATH", "ordered")
+    monkeypatch.setenv("EVREP_TAF_PATH", "sliced")
 
 
-@pytest.mark.parametrize("path", ["ordered", "bucketed"])
+@pytest.mark.parametrize("path", ["ordered", "sliced", "bucketed"])
 @pytest.mark.parametrize("K", [8, 4])
 def test_native_1mp_grid_against_oracle(K, path, monkeypatch):
     """720 x 1280 without down-scaling: more tiles than resident CTAs (several waves), a fresh window
@@ -129,7 +138,7 @@ def test_native_1mp_grid_against_oracle(K, path, monkeypatch):
     assert close(state, want_state)
 
 
-@pytest.mark.parametrize("path", ["ordered", "bucketed"])
+@pytest.mark.parametrize("path", ["ordered", "sliced", "bucketed"])
 def test_k4_gen4_policy_against_oracle(path, monkeypatch):
     """K = 4 on the down-scaled 512 x 640 grid (gen4 policy: float64 scale, truncation)."""
     monkeypatch.setenv("EVREP_TAF_PATH", path)
@@ -166,9 +175,11 @@ def test_uint8_straight_from_the_tile_kernel(ordered_path):
     assert torch.equal(u8, u8b) and torch.equal(state, state2)
 
 
-def test_unordered_input_is_detected_and_routed(ordered_path):
+@pytest.mark.parametrize("path", ["ordered", "sliced"])
+def test_unordered_input_is_detected_and_routed(path, monkeypatch):
     """A stream with a few timestamps out of order: `is_ordered` sends it to the general path (oracle
-    parity); forcing it through the ordered entry point reports the violations."""
+    parity); forcing it through an ordered entry point reports the violations."""
+    monkeypatch.setenv("EVREP_TAF_PATH", path)
     H, W, K, abin = 24, 40, 8, 1000
     rng = np.random.Generator(np.random.PCG64(13))
     n = 20000
@@ -188,6 +199,23 @@ def test_unordered_input_is_detected_and_routed(ordered_path):
     assert ops.order_violations(DEV) > 0
 
 
+def test_large_windows_fall_back_to_the_general_path(monkeypatch):
+    """A window of more than 128 slices is refused by the one-pass path: `taf_stream` routes it to the two-pass one."""
+    monkeypatch.setenv("EVREP_TAF_PATH", "ordered")
+    H, W, K, abin = 32, 48, 8, 10000
+    rng = np.random.Generator(np.random.PCG64(23))
+    n = ops.TAF_ORDERED_MAX_WINDOW + 5000
+    t = np.sort(rng.integers(0, 20000, n)).astype(np.uint32)
+    x = rng.integers(0, W, n).astype(np.uint16); y = rng.integers(0, H, n).astype(np.uint16); p = rng.integers(0, 2, n).astype(np.uint8)
+    windows = [(0, n, 0, 2, 1)]
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    state = ops.taf_fresh_state((H, W), K, DEV)
+    got = ops.taf_stream(ev, windows, abin, (H, W), K, state)
+    want, want_state = oracle_taf_windows(t, x, y, p, windows, abin, (H, W), K)
+    assert close(got[0], want[0]) and close(state, want_state)
+    assert int(ops.order_violations_tensor(DEV).abs().sum()) == 0          # no ordered call was made
+
+
 def test_long_window_rebases_inside(ordered_path):
     """One fresh window of 100 non-empty bins: the lazy ageing counter is folded back every 8 bins."""
     H, W, K, abin = 24, 40, 8, 1000
@@ -205,8 +233,10 @@ def test_long_window_rebases_inside(ordered_path):
     assert close(got[0], want[0]) and close(state, want_state)
 
 
-def test_degenerate_inputs(ordered_path):
+@pytest.mark.parametrize("path", ["ordered", "sliced"])
+def test_degenerate_inputs(path, monkeypatch):
     """Windows without bins, windows without events, an empty stream: the state is emitted unchanged."""
+    monkeypatch.setenv("EVREP_TAF_PATH", path)
     H, W, K = 16, 24, 8
     t = np.arange(0, 5000, 5, dtype=np.uint32)
     n = len(t)
