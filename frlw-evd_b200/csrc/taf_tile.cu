@@ -10,12 +10,14 @@
 // "did any pixel see an event in this bin" (generate_taf.py:40-41), is a per-bin flag produced by
 // the bucketing pass.
 //
-// Two kernels: taf_tile_ws_kernel (warp specialised, the default) and taf_tile_kernel (single
-// role; fallback when the staging tile does not fit next to two accumulator buffers).
+// Three kernels: taf_tile_ws_kernel (warp specialised, the default), taf_tile_kernel (single role; fallback when the
+// staging tile does not fit next to two accumulator buffers) and taf_tile_pk_kernel (packed accumulators, opt-in).
 //
 // HBM-bound byte/float work: no tensor cores.  Sums of d are exact integers, so the result does
 // not depend on the order in which records are accumulated.
 #include "stream_common.cuh"
+
+#include <type_traits>
 
 namespace evrep {
 
@@ -29,6 +31,7 @@ struct TileParams {
     int bulk_out;          // out rows are 16-byte aligned: emit through smem + TMA bulk stores
     float span;            // f32(abin + 1e-8)
     const uint32_t* src;   // bin-major records (kRuns kernels): first record of the (tile, bin) run, [n_tiles][TB]
+    uint32_t pk_hotmask[33];   // packed accumulators with c count bits: count bits that mark a cell whose sum of d may not be exact
 };
 
 // Shared-memory carve-up of the tile kernel (all offsets multiples of 128 bytes).
@@ -663,6 +666,469 @@ taf_tile_ws_kernel(TileParams tp) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// taf_tile_pk_kernel: the warp-specialised kernel with PACKED accumulators (opt-in: EVREP_TAF_TILE_KERNEL=pk).
+//
+// Measured on the ws kernel with in-kernel cycle counters (tools/diag_tile_timing.py): the accumulate warps, not the
+// consumers, were the critical path -- two shared-memory atomics per record on 8-byte cells (16 usable banks: ~5-way
+// conflicts), the TMA refills issued by accumulate thread 0 (~350 cycles per bin) and record chunks that arrived late
+// behind the bursts of window stores (16 KB ring).  Here:
+//   * one accumulator word per (pixel, polarity): {sum d : 32 - c | n : c}, ONE atomic per record on 4-byte cells.  c is
+//     chosen per (tile, bin) hand-over so that the count field cannot overflow (c = 10 up to 1023 records, one more bit
+//     per doubling); the sum field is exact whenever n <= nmax(c) = (2^(32-c) - 1) / (abin - 1) (419 for 10 ms bins and
+//     c = 10), and a consumer warp that finds a larger count (a hot pixel) recomputes that cell's sum from the bin's
+//     records in global memory, so results stay exact for every input;
+//   * the accumulators are half as large, which pays for THREE buffers (the accumulate warps run two bins ahead) and a
+//     32 KB record ring;
+//   * the store warp issues the record TMA loads as well (it polls a `drained` word the accumulate warps publish), and
+//     all hand-overs are mbarriers: nobody but the waiting side blocks.
+// The arithmetic (FIFO push / ageing, window tensor, state) is the ws kernel's, bit for bit.
+// Measured (tools/taf_tile_variants.py, profiles/r2_tile_variants.txt): 0.78 vs 1.06 ms at 30 Mev/s (2000 records per
+// (tile, bin): the ws kernel's accumulate warps are the limit there), but 1.12 vs 1.04 ms on the 10 Mev/s headline stream
+// (the consumers are bound by the ALU pipe either way and unpacking costs them two more instructions per cell), and several
+// times slower when moving edges put >= 32 events per bin on many cells (every such cell is rescanned).  Hence opt-in.
+constexpr int kPkStages = 16;
+constexpr int kPkRing = kWsChunkRecords * kPkStages;
+static_assert((kPkRing & (kPkRing - 1)) == 0, "ring size must be a power of two");
+constexpr int kPkBufs = 3;
+constexpr int kPkMinCountBits = 10;
+
+struct TileSmemPK {
+    int ring, acc, stage, bars, info, feed_p, total;
+    __host__ __device__ TileSmemPK(int P, int K) {
+        int o = 0;
+        ring = o;   o += kPkStages * kWsChunkRecords * 4;
+        acc = o;    o += kPkBufs * 2 * P * 4;                       // three buffers of one word per (pixel, polarity)
+        stage = o;  o += 2 * K * P * 4;                             // [2K][P] output staging
+        bars = o;   o += (kPkStages + 2 * kPkBufs + 2) * 8;
+        info = o;   o += kPkBufs * 16 + 16;                         // per buffer {first record, records, count bits, nmax}; drained chunks
+        feed_p = o; o += (TileSmemWS::kFeedBytes + 15) / 16 * 16;
+        total = o;
+    }
+};
+
+#ifdef EVREP_TILE_TIMING
+// Diagnostic build only, cycles per tile CTA: [0] accumulate thread 0 total, [1] waiting for record chunks, [2] preload +
+// producers' barrier, [3] waiting for the accumulator buffer, [4] atomics + hand-over, [5] batch feed; [8] consumer thread 0
+// total, [9] waiting for FULL, [10] read + clear, [11] update, [12] waiting for the staging tile, [13] staging.
+__device__ unsigned long long g_tile_timing[1024][16];
+#define TT_DECL long long tt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long tt_start = clock64(); long long tq = tt_start
+#define TT_MARK() do { tq = clock64(); } while (0)
+#define TT_ADD(slot) do { const long long now_ = clock64(); tt[slot] += now_ - tq; tq = now_; } while (0)
+#else
+#define TT_DECL
+#define TT_MARK()
+#define TT_ADD(slot)
+#endif
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// Warp-cooperative exact sum of d over the records of one hand-over that fall on `cell` (hot pixels only).
+__device__ __noinline__ uint32_t pk_rescan(const uint32_t* recs, uint32_t count, uint32_t cell) {
+    uint32_t tot = 0;
+    for (uint32_t i = threadIdx.x & 31u; i < count; i += 32u) {
+        const uint32_t rec = __ldg(recs + i);
+        if ((rec & 0x3FFFu) == cell) tot += rec >> 14;
+    }
+    return __reduce_add_sync(0xFFFFFFFFu, tot);
+}
+
+template <int K, int SLOTS>
+__global__ void __launch_bounds__(kWsThreads, 1)
+taf_tile_pk_kernel(TileParams tp) {
+    const StreamPlan& pl = tp.pl;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TileSmemPK lay(pl.P, K);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + lay.ring);     // [kPkStages][kWsChunkRecords]
+    uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw + lay.acc);       // [kPkBufs][2P]
+    float* stage = reinterpret_cast<float*>(smem_raw + lay.stage);         // [2K][P]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);     // [kPkStages] record chunks
+    uint64_t* acc_full = full + kPkStages;                                 // [kPkBufs] accumulate warps -> consumers
+    uint64_t* acc_empty = acc_full + kPkBufs;                              // [kPkBufs] consumers -> accumulate warps
+    uint64_t* staged = acc_empty + kPkBufs;                                // consumers -> store warp
+    uint64_t* stage_free = staged + 1;                                     // store warp -> consumers
+    volatile uint32_t* info = reinterpret_cast<volatile uint32_t*>(smem_raw + lay.info);   // [kPkBufs][4]
+    volatile uint32_t* drained_w = info + kPkBufs * 4;
+
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int64_t HW = (int64_t)pl.H * pl.W;
+    const int64_t pix0 = (int64_t)tile * pl.P;
+    const int npix = (int)min((int64_t)pl.P, HW - pix0);
+    const uint32_t* my_off = pl.off_rel + (int64_t)tile * (pl.TB + 1);
+
+    if (tid == 0) {
+        for (int s = 0; s < kPkStages; ++s) mbar_init(full + s, 1);
+        for (int b = 0; b < kPkBufs; ++b) { mbar_init(acc_full + b, kAccumThreads / 32); mbar_init(acc_empty + b, kConsumerThreads / 32); }
+        mbar_init(staged, kConsumerThreads / 32);
+        mbar_init(stage_free, 1);
+        *drained_w = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < kPkBufs * 2 * pl.P; i += kWsThreads) acc[i] = 0u;
+    __syncthreads();
+
+    if (tid < kProducerThreads) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (tid >= kAccumThreads) {
+            // ================================== store warp ==================================
+            // Keeps the record ring full (TMA loads into the stages the accumulate warps have drained) and sends the
+            // window tensors the consumers stage (TMA bulk stores).
+            const int lane = tid - kAccumThreads;
+            const uint32_t* my_records = pl.records + pl.tile_base[tile];
+            const uint32_t list_len = (pl.tile_total[tile] + 3u) & ~3u;
+            const int n_chunks = (int)((list_len + kWsChunkRecords - 1) / kWsChunkRecords);
+            const int n_emits = tp.bulk_out ? tp.n_emits : 0;
+            int issued = 0, emitted = 0, j = 0;
+            while (issued < n_chunks || emitted < n_emits) {
+                bool worked = false;
+                if (issued < n_chunks) {
+                    const int limit = min(n_chunks, (int)*drained_w + kPkStages);
+                    if (limit > issued) {
+                        if (lane == 0)
+                            for (int c = issued; c < limit; ++c) {
+                                const uint32_t first = (uint32_t)c * kWsChunkRecords;
+                                const uint32_t bytes = min((uint32_t)kWsChunkRecords, list_len - first) * 4u;
+                                uint64_t* bar = full + (c % kPkStages);
+                                mbar_expect_tx(bar, bytes);
+                                tma_load_1d(ring + (c % kPkStages) * kWsChunkRecords, my_records + first, bytes, bar);
+                            }
+                        __syncwarp();
+                        issued = limit;
+                        worked = true;
+                    }
+                }
+                if (emitted < n_emits) {
+                    const bool ready = __shfl_sync(0xFFFFFFFFu, (int)mbar_test(staged, (uint32_t)emitted & 1u), 0) != 0;
+                    if (ready) {
+                        while (!(pl.batches[j].flags & 2)) ++j;
+                        const Batch m = pl.batches[j];
+                        ++j;
+                        if (lane < 2 * K) {
+                            float* o = tp.out + (int64_t)m.win * tp.out_stride + pix0;
+                            bulk_store_1d(o + (int64_t)lane * HW, stage + lane * pl.P, (uint32_t)npix * 4u);
+                            bulk_commit();
+                            bulk_wait_read();                        // the rows have left shared memory
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(stage_free);
+                        ++emitted;
+                        worked = true;
+                    }
+                }
+                if (!worked) __nanosleep(32);
+            }
+            if (lane < 2 * K) bulk_wait_all();
+            return;
+        }
+        // ================================ accumulate warps ================================
+        BatchFeed feed;
+        feed.init(smem_raw + lay.feed_p, &pl, my_off, tid, kBarProducers, kAccumThreads);
+        const uint32_t base_idx = pl.tile_base[tile];
+        int ready_chunk = -1, buf = 0;
+        uint32_t round = 0;                                          // times the buffers have gone round
+        TT_DECL;
+        for (int j = 0; j < pl.n_batches; ++j) {
+            TT_MARK();
+            const Batch meta = feed.begin(j);
+            TT_ADD(5);
+            const int jb = j & 1;
+            for (int b = 0; b < meta.nb; ++b) {
+                const uint32_t o0 = feed.s_off[jb * (kBatchBins + 1) + b], o1 = feed.s_off[jb * (kBatchBins + 1) + b + 1];
+                if (!feed.s_any[jb * kBatchBins + b] || o1 <= o0) continue;
+                // count bits of this hand-over: the count field holds every record of the bin
+                int cbits = kPkMinCountBits;
+                while (cbits < 32 && (o1 - o0) >> cbits) ++cbits;
+                uint32_t* my_acc = acc + buf * 2 * pl.P;
+                constexpr int kPre = 8;
+                constexpr uint32_t kNoRec = 0xFFFFFFFFu;            // d = 2^18-1, pixel 8191: never produced for P <= 2560
+                // the bin goes through the registers in pieces of kPre x 96 records (one piece for all but dense bins)
+                for (uint32_t q0 = o0; q0 < o1; q0 += kPre * kAccumThreads) {
+                    const uint32_t q1 = min(o1, q0 + (uint32_t)(kPre * kAccumThreads));
+                    const int last_c = (int)((q1 - 1) / kWsChunkRecords);
+                    TT_MARK();
+                    while (ready_chunk < last_c) {
+                        ++ready_chunk;
+                        mbar_wait(full + (ready_chunk % kPkStages), (uint32_t)(ready_chunk / kPkStages) & 1u);
+                    }
+                    TT_ADD(1);
+                    // records are pulled into registers BEFORE waiting for the accumulator buffer
+                    uint32_t pre[kPre];
+                    const int n_pre = (int)((q1 - q0 + kAccumThreads - 1) / kAccumThreads);
+                    const bool small_bin = SLOTS <= 2 && n_pre <= 2;        // GEN1-size grids: ~70 records per bin
+                    if (small_bin) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const uint32_t r = q0 + tid + i * kAccumThreads;
+                            pre[i] = (i < n_pre && r < q1) ? ring[r & (kPkRing - 1)] : kNoRec;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kPre; ++i) {
+                            const uint32_t r = q0 + tid + i * kAccumThreads;
+                            pre[i] = r < q1 ? ring[r & (kPkRing - 1)] : kNoRec;
+                        }
+                    }
+                    // every accumulate thread is done with the ring up to q1: tell the store warp
+                    named_sync(kBarProducers, kAccumThreads);
+                    if (tid == 0) *drained_w = q1 / kWsChunkRecords;
+                    TT_ADD(2);
+                    if (q0 == o0) {
+                        if (round > 0) mbar_wait(acc_empty + buf, (round - 1u) & 1u);   // the consumers have drained this buffer
+                        if (tid == 0) {
+                            info[buf * 4 + 0] = base_idx + o0;
+                            info[buf * 4 + 1] = o1 - o0;
+                            info[buf * 4 + 2] = (uint32_t)cbits;
+                            info[buf * 4 + 3] = tp.pk_hotmask[cbits];
+                        }
+                    }
+                    TT_ADD(3);
+                    if (small_bin) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            if (pre[i] != kNoRec) atomicAdd(my_acc + (pre[i] & 0x3FFFu), ((pre[i] >> 14) << cbits) + 1u);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kPre; ++i)
+                            if (pre[i] != kNoRec) atomicAdd(my_acc + (pre[i] & 0x3FFFu), ((pre[i] >> 14) << cbits) + 1u);
+                    }
+                    TT_ADD(4);
+                }
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(acc_full + buf);              // hand the accumulator to the consumers
+                if (++buf == kPkBufs) { buf = 0; ++round; }
+            }
+            TT_MARK();
+            feed.end(j);
+            TT_ADD(5);
+        }
+#ifdef EVREP_TILE_TIMING
+        if (tid == 0) {
+            g_tile_timing[tile][0] = clock64() - tt_start;
+            for (int i = 1; i < 8; ++i) g_tile_timing[tile][i] = tt[i];
+        }
+#endif
+        return;
+    }
+
+    // =================================== consumer warpgroups ===================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int ctid = tid - kProducerThreads;
+    static_assert(K % 4 == 0, "K must be a multiple of 4");
+    float2 v[SLOTS][2][K / 2];
+    const bool first_fresh = (pl.batches[0].flags & 1) != 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int lp = s * kConsumerThreads + ctid;
+        if (lp < npix && !first_fresh) {
+            const float4* src = reinterpret_cast<const float4*>(tp.state + (pix0 + lp) * 2 * K);
+#pragma unroll
+            for (int q = 0; q < 2 * K / 4; ++q) {
+                const float4 f = src[q];
+                v[s][(q * 4) / K][((q * 4) % K) / 2 + 0] = make_float2(f.x, f.y);
+                v[s][(q * 4) / K][((q * 4) % K) / 2 + 1] = make_float2(f.z, f.w);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int k = 0; k < K / 2; ++k) v[s][p][k] = make_float2(kTafInit, kTafInit);
+        }
+    }
+    const uint32_t* my_bits = pl.tile_bits + (int64_t)tile * pl.n_batches;
+    Batch meta = pl.batches[0];
+    uint32_t bits = my_bits[0];
+    int buf = 0, emitted = 0;
+    uint32_t round = 0;
+    const float2 minus1 = make_float2(-1.0f, -1.0f);
+    TT_DECL;
+    for (int j = 0; j < pl.n_batches; ++j) {
+        Batch nmeta = meta;
+        uint32_t nbits = 0;
+        if (j + 1 < pl.n_batches) { nmeta = pl.batches[j + 1]; nbits = my_bits[j + 1]; }
+        if (meta.flags & 1) {
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int k = 0; k < K / 2; ++k) v[s][p][k] = make_float2(kTafInit, kTafInit);
+        }
+        for (int b = 0; b < meta.nb; ++b) {
+            if (!((bits >> (16 + b)) & 1u)) continue;               // nobody saw an event: no ageing
+            if (!((bits >> b) & 1u)) {
+                // the tile saw nothing in this bin, but some other tile did: everything ages
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+                    for (int p = 0; p < 2; ++p)
+#pragma unroll
+                        for (int k = 0; k < K / 2; ++k) v[s][p][k] = __fadd2_rn(v[s][p][k], minus1);
+                continue;
+            }
+            TT_MARK();
+            mbar_wait(acc_full + buf, round & 1u);                   // the accumulate warps filled this buffer
+            TT_ADD(9);
+            uint32_t* my_acc = acc + buf * 2 * pl.P;
+            const uint32_t cbits = info[buf * 4 + 2], hotmask = info[buf * 4 + 3];
+            uint2 w[SLOTS];
+            uint32_t seen = 0u;
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int lp = s * kConsumerThreads + ctid;
+                w[s] = make_uint2(0u, 0u);
+                if (s < SLOTS - 1 || lp < pl.P) {                    // every slot but the last lies inside the array
+                    w[s] = *reinterpret_cast<uint2*>(my_acc + 2 * lp);
+                    if (w[s].x | w[s].y) *reinterpret_cast<uint2*>(my_acc + 2 * lp) = make_uint2(0u, 0u);
+                }
+                seen |= w[s].x | w[s].y;
+            }
+            const uint32_t cmask = cbits >= 32u ? 0xFFFFFFFFu : (1u << cbits) - 1u;
+            // one test per thread: some count has a bit at or above the power of two below nmax(c) + 1
+            const bool any_hot = __any_sync(0xFFFFFFFFu, (seen & hotmask) != 0u);
+            // FIFO push / ageing of the tile's cells; kFix: the sums of hot cells come from `fix`
+            uint32_t fix[SLOTS][2];
+            auto update = [&](auto use_fix) {
+                constexpr bool kFix = decltype(use_fix)::value;
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        // mean(t_norm) - 1 = S / (n span) - 1 (generate_taf.py:23-27); NaN for n == 0, never selected
+                        const uint32_t word = p ? w[s].y : w[s].x;
+                        const uint32_t n = word & cmask;
+                        uint32_t sd = cbits >= 32u ? 0u : word >> cbits;
+                        if (kFix && (n & hotmask)) sd = fix[s][p];
+                        const bool active = n != 0u;
+                        float r;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)n * tp.span));
+                        const float mean = fmaf((float)sd, r, -1.0f);
+                        float2 aged[K / 2];
+#pragma unroll
+                        for (int k = 0; k < K / 2; ++k) aged[k] = __fadd2_rn(v[s][p][k], minus1);
+#pragma unroll
+                        for (int k = 0; k < K / 2; ++k) {
+                            const float next = (k + 1 < K / 2) ? aged[k + 1].x : mean;
+                            v[s][p][k].x = active ? aged[k].y : aged[k].x;
+                            v[s][p][k].y = active ? next : aged[k].y;
+                        }
+                    }
+                }
+            };
+            if (any_hot) {
+                // a count beyond the exact range of the packed sum: recompute those sums from the bin's records
+                const uint32_t* recs = pl.records + info[buf * 4 + 0];
+                const uint32_t i_count = info[buf * 4 + 1];
+                const int warp_ctid = ctid & ~31;
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        fix[s][p] = 0u;
+                        uint32_t mask = __ballot_sync(0xFFFFFFFFu, ((p ? w[s].y : w[s].x) & cmask & hotmask) != 0u);
+                        while (mask) {
+                            const int src = __ffs(mask) - 1;
+                            mask &= mask - 1u;
+                            const uint32_t cell = 2u * (uint32_t)(s * kConsumerThreads + warp_ctid + src) + (uint32_t)p;
+                            const uint32_t tot = pk_rescan(recs, i_count, cell);
+                            if ((ctid & 31) == src) fix[s][p] = tot;
+                        }
+                    }
+            }
+            __syncwarp();
+            if ((ctid & 31) == 0) mbar_arrive(acc_empty + buf);      // clean again (and its records no longer needed): give it back
+            TT_ADD(10);
+            if (++buf == kPkBufs) { buf = 0; ++round; }
+            if (any_hot) update(std::true_type{});
+            else update(std::false_type{});
+            TT_ADD(11);
+        }
+        if (meta.flags & 2) {
+            const bool write_state = tp.emit_state || (j == pl.n_batches - 1);
+            if (tp.bulk_out) {
+                // stage the [2K][P] tile; the store warp sends it
+                TT_MARK();
+                if (emitted > 0) mbar_wait(stage_free, (uint32_t)(emitted - 1) & 1u);
+                TT_ADD(12);
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int lp = s * kConsumerThreads + ctid;
+                    if (s == SLOTS - 1 && lp >= pl.P) continue;     // columns >= npix are staged but never stored
+#pragma unroll
+                    for (int k = 0; k < K / 2; ++k)
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            stage[(4 * k + p) * pl.P + lp] = v[s][p][k].x;
+                            stage[(4 * k + 2 + p) * pl.P + lp] = v[s][p][k].y;
+                        }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if ((ctid & 31) == 0) mbar_arrive(staged);
+                TT_ADD(13);
+                ++emitted;
+            } else {
+                float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int lp = s * kConsumerThreads + ctid;
+                    if (lp >= npix) continue;
+#pragma unroll
+                    for (int k = 0; k < K / 2; ++k)
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            __stcs(o + (int64_t)(4 * k + p) * HW + lp, v[s][p][k].x);
+                            __stcs(o + (int64_t)(4 * k + 2 + p) * HW + lp, v[s][p][k].y);
+                        }
+                }
+            }
+            if (write_state) {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int lp = s * kConsumerThreads + ctid;
+                    if (lp >= npix) continue;
+                    float4* dst = reinterpret_cast<float4*>(tp.state + (pix0 + lp) * 2 * K);
+#pragma unroll
+                    for (int q = 0; q < 2 * K / 4; ++q) {
+                        const float2 lo = v[s][(q * 4) / K][((q * 4) % K) / 2], hi = v[s][(q * 4) / K][((q * 4) % K) / 2 + 1];
+                        dst[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    }
+                }
+            }
+        }
+        meta = nmeta;
+        bits = nbits;
+    }
+#ifdef EVREP_TILE_TIMING
+    if (ctid == 0) {
+        g_tile_timing[tile][8] = clock64() - tt_start;
+        for (int i = 9; i < 16; ++i) g_tile_timing[tile][i] = tt[i];
+    }
+#endif
+}
+
+template <int K>
+static int launch_tiles_pk(const TileParams& tp, cudaStream_t st) {
+    const int slots = (tp.pl.P + kConsumerThreads - 1) / kConsumerThreads;
+    const size_t smem = (size_t)TileSmemPK(tp.pl.P, K).total;
+#define EVREP_TILE_PK(S)                                                                                  \
+    case S:                                                                                               \
+        EVREP_CUDA(cudaFuncSetAttribute(taf_tile_pk_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        taf_tile_pk_kernel<K, S><<<tp.pl.n_tiles, kWsThreads, smem, st>>>(tp);                            \
+        break;
+    switch (slots) {
+        EVREP_TILE_PK(1) EVREP_TILE_PK(2) EVREP_TILE_PK(3) EVREP_TILE_PK(4) EVREP_TILE_PK(5) EVREP_TILE_PK(6)
+        default: return EVREP_ERR_RANGE;
+    }
+#undef EVREP_TILE_PK
+    EVREP_LAUNCH_CHECK();
+    return EVREP_OK;
+}
+
 template <int K, bool kRuns>
 static int launch_tiles_ws(const TileParams& tp, cudaStream_t st) {
     const int slots = (tp.pl.P + kConsumerThreads - 1) / kConsumerThreads;
@@ -735,12 +1201,24 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
     tp.span = (float)((double)abin + 1e-8);
     tp.bulk_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
     tp.src = nullptr;
+    for (int c = 0; c <= 32; ++c) {
+        // the sum field (32 - c bits) is exact for counts up to nmax; cells are treated as hot from the power of two below nmax + 1
+        const uint64_t dmax = abin > 1 ? (uint64_t)abin - 1u : 1u;
+        const uint64_t nmax = c >= 32 ? 0u : (((uint64_t)1 << (32 - c)) - 1u) / dmax;
+        const uint64_t cmask = c >= 32 ? 0xFFFFFFFFull : ((uint64_t)1 << c) - 1u;
+        uint64_t T = 1;
+        while (T * 2 <= nmax + 1) T *= 2;
+        tp.pk_hotmask[c] = (uint32_t)(cmask & ~(T - 1u));
+    }
 
     const size_t smem = (size_t)TileSmem(L.P, K).total;
     if (ev_tiles_begin) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_begin), st));
-    const char* legacy = getenv("EVREP_TAF_TILE_KERNEL");            // "single" = the non-specialised kernel (A/B runs)
+    const char* legacy = getenv("EVREP_TAF_TILE_KERNEL");            // A/B runs: "single" = the non-specialised kernel, "pk"
     const bool ws = !(legacy && strcmp(legacy, "single") == 0) && (size_t)TileSmemWS(L.P, K).total <= 232448;
-    if (ws) rc = K == 8 ? launch_tiles_ws<8, false>(tp, st) : launch_tiles_ws<4, false>(tp, st);
+    // "pk" = the packed-accumulator variant: faster for 1500-3000 records per (tile, bin), slower below and with hot pixels
+    const bool pk = ws && legacy && strcmp(legacy, "pk") == 0 && (size_t)TileSmemPK(L.P, K).total <= 232448;
+    if (pk) rc = K == 8 ? launch_tiles_pk<8>(tp, st) : launch_tiles_pk<4>(tp, st);
+    else if (ws) rc = K == 8 ? launch_tiles_ws<8, false>(tp, st) : launch_tiles_ws<4, false>(tp, st);
     else rc = K == 8 ? launch_tiles<8>(tp, L.slots, smem, st) : launch_tiles<4>(tp, L.slots, smem, st);
     if (rc) return rc;
     if (ev_tiles_end) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_end), st));
@@ -784,11 +1262,20 @@ int evrep_taf_stream_ordered(const uint32_t* t, const uint16_t* x, const uint16_
     tp.span = (float)((double)abin + 1e-8);
     tp.bulk_out = (((int64_t)H * W) % 4 == 0 && out_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
     tp.src = src;
+    for (int c = 0; c <= 32; ++c) tp.pk_hotmask[c] = 0u;
     if (ev_tiles_begin) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_begin), st));
     rc = K == 8 ? launch_tiles_ws<8, true>(tp, st) : launch_tiles_ws<4, true>(tp, st);
     if (rc) return rc;
     if (ev_tiles_end) EVREP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev_tiles_end), st));
     return EVREP_OK;
 }
+
+#ifdef EVREP_TILE_TIMING
+int evrep_debug_tile_timing(unsigned long long* host, int n_tiles) {
+    EVREP_CUDA(cudaDeviceSynchronize());
+    EVREP_CUDA(cudaMemcpyFromSymbol(host, g_tile_timing, sizeof(unsigned long long) * 16 * (size_t)n_tiles));
+    return EVREP_OK;
+}
+#endif
 
 }  // extern "C"

@@ -206,11 +206,49 @@ def test_single_role_kernel_equals_warp_specialised(monkeypatch):
     maps = ops.make_coord_maps((720, 1280), (512, 640), DEV)
     windows = [(0, idx(t, 80000), 0, 8, 1), (idx(t, 80000), idx(t, 150000), 80000, 7, 0)]
     outs = []
-    for mode in ("ws", "single"):
+    for mode in ("ws", "single", "pk"):
         monkeypatch.setenv("EVREP_TAF_TILE_KERNEL", mode)
         state = ops.taf_fresh_state((512, 640), 8, DEV)
         outs.append((ops.taf_stream(ev, windows, 10000, (512, 640), 8, state, maps).clone(), state))
+    for other in outs[1:]:
+        assert torch.equal(outs[0][0], other[0]) and torch.equal(outs[0][1], other[1])
+
+
+@pytest.mark.parametrize("K", [4, 8])
+def test_packed_accumulator_kernel_hot_cells_and_dense_bins(K, monkeypatch):
+    """EVREP_TAF_TILE_KERNEL=pk packs (sum d, n) of a cell into one word.  A pixel with more events in a bin than the
+    sum field can hold exactly (> 419 at 10 ms), a bin with more records than one pass of the accumulate warps (768), more
+    than the 10-bit count field (1023) and more than the record ring (8192): all bit-identical to the ws kernel and
+    equal to the oracle."""
+    H, W, abin = 48, 64, 10000
+    rng = np.random.Generator(np.random.PCG64(77))
+    parts = []
+    def burst(n, t0, t1, hot=None):
+        t = rng.integers(t0, t1, n)
+        x = rng.integers(0, W, n); y = rng.integers(0, H, n); p = rng.integers(0, 2, n)
+        if hot is not None:
+            k = hot[0]
+            x[:k], y[:k], p[:k] = hot[1], hot[2], hot[3]
+        parts.append(np.stack([t, x, y, p], 1))
+    burst(3000, 0, 10000, hot=(700, 5, 7, 1))           # bin 0: a pixel with 700 events, 3000 records in the tile
+    burst(900, 10000, 20000)                            # bin 1: one pass + a bit
+    burst(20000, 30000, 40000, hot=(5000, 60, 40, 0))   # bin 3 (bin 2 empty): beyond the ring, a very hot pixel
+    burst(40, 40000, 50000)
+    burst(1200, 70000, 80000, hot=(430, 0, 0, 0))       # second window
+    e = np.concatenate(parts)
+    e = e[np.argsort(e[:, 0], kind="stable")]
+    t = e[:, 0].astype(np.uint32); x = e[:, 1].astype(np.uint16); y = e[:, 2].astype(np.uint16); p = e[:, 3].astype(np.uint8)
+    cut = idx(t, 50000)
+    windows = [(0, cut, 0, 5, 1), (cut, len(t), 50000, 3, 0)]
+    ev = ops.EventStream.from_numpy(t, x, y, p)
+    outs = []
+    for mode in ("ws", "pk"):
+        monkeypatch.setenv("EVREP_TAF_TILE_KERNEL", mode)
+        state = ops.taf_fresh_state((H, W), K, DEV)
+        outs.append((ops.taf_stream(ev, windows, abin, (H, W), K, state).clone(), state))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    want, want_state = oracle_taf_windows(t, x, y, p, windows, abin, (H, W), K)
+    assert close(outs[1][0][0], want[0]) and close(outs[1][0][1], want[1]) and close(outs[1][1], want_state)
 
 
 def test_stream_argument_errors():
