@@ -135,6 +135,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -187,7 +193,7 @@ struct TileSmemWS {
         ring = o;   o += kWsStages * kWsChunkRecords * 4;
         acc = o;    o += 2 * 2 * P * (int)sizeof(uint2);            // two buffers of {n, sum d} per (pixel, polarity)
         stage = o;  o += 2 * K * P * 4;                             // [2K][P] output staging
-        bars = o;   o += 64;
+        bars = o;   o += 96;            // 8 record chunks, STAGED, STAGE_FREE, the drained-chunks word
         feed_p = o; o += (kFeedBytes + 15) / 16 * 16;
         total = o;
     }

@@ -320,7 +320,10 @@ taf_tile_ws_kernel(TileParams tp) {
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + lay.ring);     // [kWsStages][kWsChunkRecords]
     uint2* acc = reinterpret_cast<uint2*>(smem_raw + lay.acc);             // [2][2P]
     float* stage = reinterpret_cast<float*>(smem_raw + lay.stage);         // [2K][P]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);     // [kWsStages] record chunks
+    uint64_t* staged = full + kWsStages;                                   // consumers -> store warp
+    uint64_t* stage_free = staged + 1;                                     // store warp -> consumers
+    volatile uint32_t* drained_w = reinterpret_cast<volatile uint32_t*>(stage_free + 1);   // ring chunks the accumulate warps are done with
 
     const int tid = threadIdx.x, tile = blockIdx.x;
     const int64_t HW = (int64_t)pl.H * pl.W;
@@ -330,6 +333,9 @@ taf_tile_ws_kernel(TileParams tp) {
 
     if (tid == 0) {
         for (int s = 0; s < kWsStages; ++s) mbar_init(full + s, 1);
+        mbar_init(staged, kConsumerThreads / 32);
+        mbar_init(stage_free, 1);
+        *drained_w = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 4 * pl.P; i += kWsThreads) acc[i] = make_uint2(0u, 0u);
@@ -339,23 +345,52 @@ taf_tile_ws_kernel(TileParams tp) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (tid >= kAccumThreads) {
             // ================================== store warp ==================================
-            // Waits for the consumers to stage a window tensor, sends its rows with TMA bulk
-            // stores and tells the consumers when the staging tile may be overwritten.
-            if (!tp.bulk_out) return;
+            // Keeps the record ring full -- TMA loads into the stages the accumulate warps have drained (they publish
+            // `drained_w`; issuing the copies from accumulate thread 0 cost that warp ~350 cycles per bin) -- and sends
+            // every window tensor the consumers stage with TMA bulk stores.  kRuns: the accumulate warps issue the loads.
             const int lane = tid - kAccumThreads;
-            int emitted = 0;
-            for (int j = 0; j < pl.n_batches; ++j) {
-                const Batch m = pl.batches[j];
-                if (!(m.flags & 2)) continue;
-                named_sync(kBarStaged, kStoreThreads + kConsumerThreads);
-                if (lane < 2 * K) {
-                    float* o = tp.out + (int64_t)m.win * tp.out_stride + pix0;
-                    bulk_store_1d(o + (int64_t)lane * HW, stage + lane * pl.P, (uint32_t)npix * 4u);
-                    bulk_commit();
-                    bulk_wait_read();                                // the rows have left shared memory
+            const uint32_t* my_records = pl.records + (kRuns ? 0u : pl.tile_base[tile]);
+            const uint32_t list_len = (pl.tile_total[tile] + 3u) & ~3u;
+            const int n_chunks = kRuns ? 0 : (int)((list_len + kWsChunkRecords - 1) / kWsChunkRecords);
+            const int n_emits = tp.bulk_out ? tp.n_emits : 0;
+            int issued = 0, emitted = 0, j = 0;
+            while (issued < n_chunks || emitted < n_emits) {
+                bool worked = false;
+                if (issued < n_chunks) {
+                    const int limit = min(n_chunks, (int)*drained_w + kWsStages);
+                    if (limit > issued) {
+                        if (lane == 0)
+                            for (int c = issued; c < limit; ++c) {
+                                const uint32_t first = (uint32_t)c * kWsChunkRecords;
+                                const uint32_t bytes = min((uint32_t)kWsChunkRecords, list_len - first) * 4u;
+                                uint64_t* bar = full + (c % kWsStages);
+                                mbar_expect_tx(bar, bytes);
+                                tma_load_1d(ring + (c % kWsStages) * kWsChunkRecords, my_records + first, bytes, bar);
+                            }
+                        __syncwarp();
+                        issued = limit;
+                        worked = true;
+                    }
                 }
-                __syncwarp();
-                if (++emitted < tp.n_emits) named_arrive(kBarStageFree, kStoreThreads + kConsumerThreads);
+                if (emitted < n_emits) {
+                    const bool ready = __shfl_sync(0xFFFFFFFFu, (int)mbar_test(staged, (uint32_t)emitted & 1u), 0) != 0;
+                    if (ready) {
+                        while (!(pl.batches[j].flags & 2)) ++j;
+                        const Batch m = pl.batches[j];
+                        ++j;
+                        if (lane < 2 * K) {
+                            float* o = tp.out + (int64_t)m.win * tp.out_stride + pix0;
+                            bulk_store_1d(o + (int64_t)lane * HW, stage + lane * pl.P, (uint32_t)npix * 4u);
+                            bulk_commit();
+                            bulk_wait_read();                        // the rows have left shared memory
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(stage_free);
+                        ++emitted;
+                        worked = true;
+                    }
+                }
+                if (!worked) __nanosleep(32);
             }
             if (lane < 2 * K) bulk_wait_all();
             return;
@@ -396,7 +431,7 @@ taf_tile_ws_kernel(TileParams tp) {
                 cur = piece_end;
             }
         };
-        if (tid == 0)
+        if (kRuns && tid == 0)
             for (int c = 0; c < n_chunks && c < kWsStages; ++c) issue(c);
         BatchFeed feed;
         feed.init(smem_raw + lay.feed_p, &pl, my_off, tid, kBarProducers, kAccumThreads);
@@ -449,8 +484,12 @@ taf_tile_ws_kernel(TileParams tp) {
                     {
                         // ring stages whose chunk ends before the first record still to be read are free
                         const int drained = (int)((all_pre ? o1 : o0) / kWsChunkRecords);
-                        if (tid == 0)
-                            for (int r = next_refill; r < drained + kWsStages && r < n_chunks; ++r) issue(r);
+                        if (kRuns) {
+                            if (tid == 0)
+                                for (int r = next_refill; r < drained + kWsStages && r < n_chunks; ++r) issue(r);
+                        } else if (tid == 0) {
+                            *drained_w = (uint32_t)drained;           // the store warp refills them
+                        }
                         if (drained + kWsStages > next_refill) next_refill = drained + kWsStages;
                     }
                     if (small_bin) {
@@ -489,9 +528,15 @@ taf_tile_ws_kernel(TileParams tp) {
                         const uint32_t seg_end = o1 < chunk_end ? o1 : chunk_end;
                         if (c >= next_refill) {
                             named_sync(kBarProducers, kAccumThreads);
-                            if (tid == 0)
-                                for (int r = next_refill; r <= c && r < n_chunks; ++r) issue(r);
-                            next_refill = c + 1;
+                            if (kRuns) {
+                                if (tid == 0)
+                                    for (int r = next_refill; r <= c && r < n_chunks; ++r) issue(r);
+                                next_refill = c + 1;
+                            } else {
+                                // everything before `cur` has been read by every accumulate thread
+                                if (tid == 0) *drained_w = cur / kWsChunkRecords;
+                                next_refill = (int)(cur / kWsChunkRecords) + kWsStages;
+                            }
                         }
                         while (ready_chunk < c) {
                             ++ready_chunk;
@@ -616,7 +661,7 @@ taf_tile_ws_kernel(TileParams tp) {
             if (tp.bulk_out) {
                 // stage the [2K][P] tile; the store warp sends it.  No consumer waits for another:
                 // each warp streams its columns, fences, signals and moves on to the next bin.
-                if (emitted > 0) named_sync(kBarStageFree, kStoreThreads + kConsumerThreads);
+                if (emitted > 0) mbar_wait(stage_free, (uint32_t)(emitted - 1) & 1u);
 #pragma unroll
                 for (int s = 0; s < SLOTS; ++s) {
                     const int lp = s * kConsumerThreads + ctid;
@@ -630,7 +675,8 @@ taf_tile_ws_kernel(TileParams tp) {
                         }
                 }
                 fence_async_smem();
-                named_arrive(kBarStaged, kStoreThreads + kConsumerThreads);
+                __syncwarp();
+                if ((ctid & 31) == 0) mbar_arrive(staged);
                 ++emitted;
             } else {
                 float* o = tp.out + (int64_t)meta.win * tp.out_stride + pix0;
@@ -721,12 +767,6 @@ __device__ unsigned long long g_tile_timing[1024][16];
 #define TT_ADD(slot)
 #endif
 
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
 
 // Warp-cooperative exact sum of d over the records of one hand-over that fall on `cell` (hot pixels only).
 __device__ __noinline__ uint32_t pk_rescan(const uint32_t* recs, uint32_t count, uint32_t cell) {
