@@ -80,6 +80,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.max_mhz, self._halt, self._armed = index, None, threading.Event(), threading.Event()
         self.regions, self._region, self.error = {}, None, None
+        self.ready = threading.Event()          # NVML is up: samples start within a millisecond of arm()
 
     def run(self):
         try:
@@ -87,6 +88,7 @@ class ClockSampler(threading.Thread):
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.ready.set()
             while not self._halt.is_set():
                 if not self._armed.wait(0.05):
                     continue
@@ -96,6 +98,7 @@ class ClockSampler(threading.Thread):
                 self._halt.wait(0.001)
         except Exception as exc:          # clocks are evidence, not a dependency
             self.error = repr(exc)
+            self.ready.set()
 
     def arm(self, region):
         self.regions.setdefault(region, {"mhz": [], "mask": 0})
@@ -339,6 +342,7 @@ def main():
         step()
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.ready.wait(10.0)
     barrier()
     sampler.arm("device")
     start.record()

@@ -366,6 +366,11 @@ taf_tile_ws_kernel(TileParams tp) {
                                 uint64_t* bar = full + (c % kWsStages);
                                 mbar_expect_tx(bar, bytes);
                                 tma_load_1d(ring + (c % kWsStages) * kWsChunkRecords, my_records + first, bytes, bar);
+                                // DRAM reads queue behind the window stores for microseconds and the ring holds 16 KB:
+                                // pull the chunk kWsPrefetch ahead into L2 now
+                                const uint32_t ahead = first + kWsPrefetch * kWsChunkRecords;
+                                if (ahead < list_len)
+                                    l2_prefetch(my_records + ahead, min((uint32_t)kWsChunkRecords, list_len - ahead) * 4u);
                             }
                         __syncwarp();
                         issued = limit;
