@@ -195,8 +195,8 @@ int evrep_taf_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, co
                      void* scratch, int64_t scratch_bytes,
                      void* ev_tiles_begin, void* ev_tiles_end, evrep_stream_t stream);
 
-/* ------------- T2 (time-ordered input, the fast path): one-pass bin-major sort + the tile kernel of evrep_taf_stream
- * Same contract and results as evrep_taf_stream for streams whose timestamps are non-decreasing over
+/* ------------- T2 (time-ordered input, bin-major variant): one-pass sort + the tile kernel of evrep_taf_stream ------
+ * Measured slower than evrep_taf_stream; kept as an alternative.  Same contract and results as evrep_taf_stream for streams whose timestamps are non-decreasing over
  * [windows[0].ev_begin, windows[n-1].ev_end).  Every bin of a window is then one contiguous index range: the bins'
  * ranges come from bisection, every bin is cut into slices of <= 8188 events, one CTA sorts a slice by sensor tile in
  * shared memory, the CTAs of a bin's slices exchange their tile counts and write every (bin, tile) run contiguously
