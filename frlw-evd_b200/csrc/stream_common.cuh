@@ -178,7 +178,7 @@ constexpr int kWsThreads = kProducerThreads + kConsumerThreads;
 constexpr int kWsChunkRecords = 512;    // 2 KB TMA bulk copies
 constexpr int kWsStages = 8;            // 16 KB ring = a flat circular buffer of 4096 records
 constexpr int kWsRing = kWsChunkRecords * kWsStages;
-constexpr int kWsPrefetch = 32;         // chunks (64 KB) the store warp prefetches into L2 ahead of the ring
+constexpr int kWsPrefetch = 8;          // chunks (16 KB, one ring) the store warp prefetches into L2 ahead of the ring
 static_assert((kWsRing & (kWsRing - 1)) == 0, "ring size must be a power of two");
 
 enum : int { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarProducers = 6, kBarStaged = 7, kBarStageFree = 8 };
