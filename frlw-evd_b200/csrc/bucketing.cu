@@ -144,12 +144,38 @@ constexpr uint32_t kKeyFar = 0xFFFEu, kKeyDropped = 0xFFFFu;     // saved keys t
 template <int kMode>
 __global__ void __launch_bounds__(kBucketThreads, 2)
 taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int n_chunks, int lut_w, int lut_h,
-                  const ChunkOrigin* __restrict__ origins, int vec_ok) {
+                  const ChunkOrigin* __restrict__ origins, int vec_ok, int stage_ok) {
     constexpr bool kScatter = kMode == kModeScatter;
     constexpr bool kSave = kMode == kModeCountSave;
-    extern __shared__ __align__(16) unsigned char bsm[];
+    extern __shared__ __align__(128) unsigned char bsm[];
     const int nh = kLocalBins * pl.n_tiles;
     const BucketSmem lay(lut_w, lut_h, nh, kScatter);
+    // Count + save pass: a CTA's NEXT full chunk is copied into shared memory by TMA bulk copies while the current one is
+    // classified (stage_ok: the event arrays are 16-byte aligned), so that no thread waits for DRAM: a quarter of this
+    // kernel's stall samples were the first use of the chunk's global loads.
+    constexpr uint32_t kChunkEvents = kBucketThreads * kBucketPerThread;
+    unsigned char* stage = bsm + (lay.total + 127) / 128 * 128;          // t (4 B), x (2 B), y (2 B), p (1 B) per event
+    const uint32_t* st_t = reinterpret_cast<const uint32_t*>(stage);
+    const uint16_t* st_x = reinterpret_cast<const uint16_t*>(stage + kChunkEvents * 4);
+    const uint16_t* st_y = reinterpret_cast<const uint16_t*>(stage + kChunkEvents * 6);
+    const uint8_t* st_p = stage + kChunkEvents * 8;
+    __shared__ __align__(8) uint64_t stage_bar;
+    const bool staging = kSave && stage_ok != 0;
+    auto stage_issue = [&](int chunk) {                                   // thread 0: full chunks only
+        const int64_t b0 = ev_first + (int64_t)chunk * kChunkEvents;
+        if (chunk >= n_chunks || b0 + kChunkEvents > ev_last) return;
+        mbar_expect_tx(&stage_bar, kChunkEvents * 9u);
+        tma_load_1d(stage, ev.t + b0, kChunkEvents * 4u, &stage_bar);
+        tma_load_1d(stage + kChunkEvents * 4, ev.x + b0, kChunkEvents * 2u, &stage_bar);
+        tma_load_1d(stage + kChunkEvents * 6, ev.y + b0, kChunkEvents * 2u, &stage_bar);
+        tma_load_1d(stage + kChunkEvents * 8, ev.p + b0, kChunkEvents, &stage_bar);
+    };
+    if (staging && threadIdx.x == 0) {
+        mbar_init(&stage_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        stage_issue((int)blockIdx.x);
+    }
+    uint32_t n_staged = 0;                                                // staged chunks consumed so far (barrier phase)
     uint32_t* s_col = reinterpret_cast<uint32_t*>(bsm + lay.lutx);
     uint32_t* s_row = reinterpret_cast<uint32_t*>(bsm + lay.luty);
     uint32_t* hist = reinterpret_cast<uint32_t*>(bsm + lay.hist);
@@ -195,7 +221,37 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
         // per event: timestamp, x | y << 16, and the polarity bytes four to a word (0xFF = no event)
         uint32_t tt[kBucketPerThread], xy[kBucketPerThread], pw[kBucketPerThread / 4];
         static_assert(kBucketPerThread % 4 == 0, "events are handled in groups of 4");
-        if (fast && vec_ok) {
+        const bool staged = staging && (c1 - c0) == kBucketThreads * kBucketPerThread;
+        if (staged) {
+            mbar_wait(&stage_bar, n_staged & 1u);
+            ++n_staged;
+            if (fast) {
+#pragma unroll
+                for (int g = 0; g < kBucketPerThread / 4; ++g) {
+                    const uint32_t base = ((uint32_t)g * kBucketThreads + threadIdx.x) * 4u;
+                    const uint4 t4 = *reinterpret_cast<const uint4*>(st_t + base);
+                    const uint2 x4 = *reinterpret_cast<const uint2*>(st_x + base);
+                    const uint2 y4 = *reinterpret_cast<const uint2*>(st_y + base);
+                    pw[g] = *reinterpret_cast<const uint32_t*>(st_p + base);
+                    tt[4 * g + 0] = t4.x; tt[4 * g + 1] = t4.y; tt[4 * g + 2] = t4.z; tt[4 * g + 3] = t4.w;
+                    xy[4 * g + 0] = __byte_perm(x4.x, y4.x, 0x5410); xy[4 * g + 1] = __byte_perm(x4.x, y4.x, 0x7632);
+                    xy[4 * g + 2] = __byte_perm(x4.y, y4.y, 0x5410); xy[4 * g + 3] = __byte_perm(x4.y, y4.y, 0x7632);
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < kBucketPerThread / 4; ++g) {
+                    uint32_t pol4 = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = 4 * g + e;
+                        const uint32_t i = (uint32_t)k * kBucketThreads + threadIdx.x;
+                        tt[k] = st_t[i]; xy[k] = st_x[i] | ((uint32_t)st_y[i] << 16);
+                        pol4 |= (uint32_t)st_p[i] << (8 * e);
+                    }
+                    pw[g] = pol4;
+                }
+            }
+        } else if (fast && vec_ok) {
             // 4 consecutive events per 128/64/64/32-bit load (c0 is a multiple of 4 events)
 #pragma unroll
             for (int g = 0; g < kBucketPerThread / 4; ++g) {
@@ -225,7 +281,8 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
             }
         }
 
-        __syncthreads();                                   // histogram is zeroed
+        __syncthreads();                                   // histogram is zeroed; the staged chunk is in registers
+        if (staging && threadIdx.x == 0) stage_issue(chunk + (int)gridDim.x);
         // per event: (smem counter << 12) | rank inside the chunk, or kNone when dropped
         constexpr uint32_t kNone = 0xFFFFFFFFu;
         uint32_t slot[kScatter ? kBucketPerThread : 1], rec[kBucketPerThread] = {};
@@ -713,9 +770,12 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
     if (TB > 0) {
         EVREP_CUDA(cudaMemsetAsync(s + L.o_counts, 0, (size_t)(L.o_offrel - L.o_counts), st));   // counts + bin_any
         // chunks start on a multiple of 4 events so that full chunks can use vector loads
-        const int64_t ev_first = windows_host[0].ev_begin & ~3ll, ev_last = windows_host[n_windows - 1].ev_end;
+        // (a multiple of 16 events: the count pass stages whole chunks with 16-byte aligned TMA bulk copies)
+        const int64_t ev_first = windows_host[0].ev_begin & ~15ll, ev_last = windows_host[n_windows - 1].ev_end;
         const int vec_ok = !((reinterpret_cast<uintptr_t>(t) & 15) | (reinterpret_cast<uintptr_t>(x) & 7) |
                              (reinterpret_cast<uintptr_t>(y) & 7) | (reinterpret_cast<uintptr_t>(p) & 3));
+        const int stage_ok = !((reinterpret_cast<uintptr_t>(t) | reinterpret_cast<uintptr_t>(x) |
+                                reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(p)) & 15);
         const int64_t per_cta = kBucketThreads * kBucketPerThread;
         const int64_t n_chunks = (ev_last - ev_first + per_cta - 1) / per_cta;
         if (n_chunks >= (1ll << 31)) return EVREP_ERR_RANGE;
@@ -725,6 +785,7 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
         const int lut_w = use_lut ? sensor_w : W, lut_h = use_lut ? sensor_h : H;
         const int nh = kLocalBins * L.n_tiles;
         const size_t smem_count = (size_t)BucketSmem(lut_w, lut_h, nh, false).total;
+        const size_t smem_save = (smem_count + 127) / 128 * 128 + (size_t)kBucketThreads * kBucketPerThread * 9;   // + the staged chunk
         const size_t smem_scatter = (size_t)BucketSmem(lut_w, lut_h, nh, true).total;
         if (smem_scatter > 100 * 1024) return EVREP_ERR_RANGE;          // two CTAs per SM
         SoA ev{t, x, y, p, xmap, ymap};
@@ -740,17 +801,17 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
             if (grid > 0) {
                 taf_chunk_origin_kernel<<<(int)((n_chunks + 255) / 256), 256, 0, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, (int)per_cta, origins);
                 EVREP_LAUNCH_CHECK();
-                taf_bucket_kernel<kModeCount><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok);
+                taf_bucket_kernel<kModeCount><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok, 0);
                 EVREP_LAUNCH_CHECK();
             }
         } else {
-            EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<kModeCountSave>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+            EVREP_CUDA(cudaFuncSetAttribute(taf_bucket_kernel<kModeCountSave>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_save));
             if (grid > 0) {
                 const int64_t n_super = (n_chunks + kScatterChunks - 1) / kScatterChunks;
                 taf_chunk_origin_kernel<<<(int)((n_super + 255) / 256), 256, 0, st>>>(ev, pl, ev_first, ev_last, (int)n_super,
                                                                                     (int)(per_cta * kScatterChunks), origins);
                 EVREP_LAUNCH_CHECK();
-                taf_bucket_kernel<kModeCountSave><<<grid, kBucketThreads, smem_count, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok);
+                taf_bucket_kernel<kModeCountSave><<<grid, kBucketThreads, smem_save, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok, stage_ok);
                 EVREP_LAUNCH_CHECK();
             }
         }
@@ -761,7 +822,7 @@ int prepare_stream(const uint32_t* t, const uint16_t* x, const uint16_t* y, cons
         taf_tile_bits_kernel<<<L.n_tiles, 256, 0, st>>>(pl);
         EVREP_LAUNCH_CHECK();
         if (grid > 0 && reclassify) {
-            taf_bucket_kernel<kModeScatter><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok);
+            taf_bucket_kernel<kModeScatter><<<grid, kBucketThreads, smem_scatter, st>>>(ev, pl, ev_first, ev_last, (int)n_chunks, lut_w, lut_h, origins, vec_ok, 0);
             EVREP_LAUNCH_CHECK();
         } else if (grid > 0) {
             const int64_t n_super = (n_chunks + kScatterChunks - 1) / kScatterChunks;
