@@ -251,6 +251,28 @@ def test_packed_accumulator_kernel_hot_cells_and_dense_bins(K, monkeypatch):
     assert close(outs[1][0][0], want[0]) and close(outs[1][0][1], want[1]) and close(outs[1][1], want_state)
 
 
+def test_stream_on_unaligned_arrays_and_window_starts():
+    """The bucketing passes use vector loads and TMA-staged chunks when the event arrays are 16-byte aligned and fall back
+    to scalar loads otherwise; chunks start on a multiple of 16 events at or before the first window.  Same tensors from
+    a stream that starts 3 events into its buffers, and for windows that begin at odd event indices."""
+    H, W, K, abin = 240, 304, 8, 10000
+    t, x, y, p = synth.make_stream(H, W, 60000, 2e6, 41)
+    n = len(t)
+    pad = 3
+    tp_, xp_, yp_, pp_ = (np.concatenate([np.zeros(pad, a.dtype), a]) for a in (t, x, y, p))
+    shifted = ops.EventStream.from_numpy(tp_, xp_, yp_, pp_).slice(pad, pad + n)
+    aligned = ops.EventStream.from_numpy(t, x, y, p)
+    a0, a1 = idx(t, 10000) + 5, idx(t, 30000)
+    windows = [(a0, a1, 10000, 2, 1), (a1, idx(t, 60000), 30000, 3, 0)]
+    outs = []
+    for ev in (aligned, shifted):
+        state = ops.taf_fresh_state((H, W), K, DEV)
+        outs.append((ops.taf_stream(ev, windows, abin, (H, W), K, state).clone(), state))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    want, want_state = oracle_taf_windows(t, x, y, p, windows, abin, (H, W), K)
+    assert close(outs[0][0][0], want[0]) and close(outs[0][0][1], want[1]) and close(outs[0][1], want_state)
+
+
 def test_stream_argument_errors():
     from frlw_evd_b200 import _lib
     t, x, y, p = synth.make_stream(240, 304, 20000, 1e6, 3)
