@@ -388,38 +388,33 @@ leaky_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
 
 // generate_taf.py:226-235: [2K,H,W] (channel 2k+p) -> u8 [K,2,Ht,Wt], slot axis flipped.
 // `n` windows at once: window w reads vol + w * vol_stride and writes out + w * 2K*Ht*Wt.
+// blockIdx.y walks the n * 2K output planes, blockIdx.x the pixels of a plane: no 64-bit division per element
+// (8 windows of 512 x 640, 168 MB read + 42 MB written: 0.094 ms).
 __global__ void __launch_bounds__(kBlock)
 taf_leaky_u8_kernel(const float* __restrict__ vol, int64_t vol_stride, int n, int K, int H, int W, int Ht, int Wt,
                     const int32_t* __restrict__ ysrc, const int32_t* __restrict__ xsrc, uint8_t* __restrict__ out) {
-    const int64_t per = (int64_t)2 * K * Ht * Wt;
-    const int64_t total = per * n;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const bool vec = !ysrc && !xsrc && (Wt % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0) &&
+    const uint32_t plane = (uint32_t)Ht * (uint32_t)Wt;
+    const int planes = n * 2 * K;
+    const bool vec = !ysrc && !xsrc && (plane % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0) &&
                      ((reinterpret_cast<uintptr_t>(vol) & 15) == 0) && (vol_stride % 4 == 0);
-    if (vec) {          // same-size grid: 4 pixels per thread, 128-bit loads, 32-bit stores
-        for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total / 4; q += stride) {
-            const int64_t i = q * 4;
-            const int64_t w = i / per, j = i - w * per;
-            const int64_t plane = (int64_t)Ht * Wt;
-            const int ch = (int)(j / plane);
-            const int64_t pix = j - ch * plane;
-            const int k = K - 1 - (ch >> 1), p = ch & 1;
-            const float4 v = __ldcs(reinterpret_cast<const float4*>(vol + w * vol_stride + (int64_t)(2 * k + p) * plane + pix));
-            const uint32_t packed = to_u8(leaky(v.x), 0) | (to_u8(leaky(v.y), 0) << 8) | (to_u8(leaky(v.z), 0) << 16) |
-                                    ((uint32_t)to_u8(leaky(v.w), 0) << 24);
-            reinterpret_cast<uint32_t*>(out)[q] = packed;
+    for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+        const int w = pl / (2 * K), ch = pl - w * 2 * K;             // destination channel 2 * slot + p
+        const int k = K - 1 - (ch >> 1), p = ch & 1;
+        const float* src = vol + (int64_t)w * vol_stride + (int64_t)(2 * k + p) * H * W;
+        uint8_t* dst = out + (int64_t)pl * plane;
+        if (vec) {      // same-size grid: 4 pixels per thread, 128-bit loads, 32-bit stores
+            for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < plane / 4; q += gridDim.x * blockDim.x) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + q);
+                reinterpret_cast<uint32_t*>(dst)[q] = to_u8(leaky(v.x), 0) | (to_u8(leaky(v.y), 0) << 8) |
+                                                      (to_u8(leaky(v.z), 0) << 16) | ((uint32_t)to_u8(leaky(v.w), 0) << 24);
+            }
+        } else {
+            for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
+                const uint32_t Y = i / (uint32_t)Wt, X = i - Y * (uint32_t)Wt;
+                const int ys = ysrc ? ysrc[Y] : (int)Y, xs = xsrc ? xsrc[X] : (int)X;
+                dst[i] = to_u8(leaky(src[(int64_t)ys * W + xs]), 0);
+            }
         }
-        return;
-    }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int64_t w = i / per, j = i - w * per;
-        int X = (int)(j % Wt);
-        int64_t r = j / Wt;
-        int Y = (int)(r % Ht);
-        int ch = (int)(r / Ht);                      // destination channel 2*slot + p
-        int k = K - 1 - (ch >> 1), p = ch & 1;
-        int ys = ysrc ? ysrc[Y] : Y, xs = xsrc ? xsrc[X] : X;
-        out[i] = to_u8(leaky(vol[w * vol_stride + ((int64_t)(2 * k + p) * H + ys) * W + xs]), 0);
     }
 }
 
@@ -717,13 +712,14 @@ int evrep_leaky_transform(const float* in, int64_t n, float* out, evrep_stream_t
     return EVREP_OK;
 }
 
+int evrep_taf_leaky_u8_batch(const float* volumes, int64_t volume_stride, int n_windows, int K, int H, int W, int Ht,
+                             int Wt, const int32_t* ysrc, const int32_t* xsrc, uint8_t* out, evrep_stream_t stream);
+
 int evrep_taf_leaky_u8(const float* volume, int K, int H, int W, int Ht, int Wt, const int32_t* ysrc,
                        const int32_t* xsrc, uint8_t* out, evrep_stream_t stream) {
     if (!volume || !out || K <= 0 || H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0) return EVREP_ERR_ARG;
     if ((!ysrc || !xsrc) && (Ht != H || Wt != W)) return EVREP_ERR_ARG;
-    taf_leaky_u8_kernel<<<grid_for((int64_t)2 * K * Ht * Wt), kBlock, 0, as_stream(stream)>>>(volume, 0, 1, K, H, W, Ht, Wt, ysrc, xsrc, out);
-    EVREP_LAUNCH_CHECK();
-    return EVREP_OK;
+    return evrep_taf_leaky_u8_batch(volume, 0, 1, K, H, W, Ht, Wt, ysrc, xsrc, out, stream);
 }
 
 int evrep_taf_leaky_u8_batch(const float* volumes, int64_t volume_stride, int n_windows, int K, int H, int W, int Ht,
@@ -731,7 +727,11 @@ int evrep_taf_leaky_u8_batch(const float* volumes, int64_t volume_stride, int n_
     if (!volumes || !out || n_windows < 0 || K <= 0 || H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0) return EVREP_ERR_ARG;
     if ((!ysrc || !xsrc) && (Ht != H || Wt != W)) return EVREP_ERR_ARG;
     if (n_windows == 0) return EVREP_OK;
-    taf_leaky_u8_kernel<<<grid_for((int64_t)2 * K * Ht * Wt * n_windows, 4), kBlock, 0, as_stream(stream)>>>(
+    const int64_t per_thread = (!ysrc && !xsrc) ? 4 : 1;
+    const int64_t bx = ((int64_t)Ht * Wt / per_thread + kBlock - 1) / kBlock;
+    const int64_t planes = (int64_t)n_windows * 2 * K;
+    const dim3 grid((unsigned)(bx < 1 ? 1 : (bx > 65535 ? 65535 : bx)), (unsigned)(planes > 65535 ? 65535 : planes));
+    taf_leaky_u8_kernel<<<grid, kBlock, 0, as_stream(stream)>>>(
         volumes, volume_stride, n_windows, K, H, W, Ht, Wt, ysrc, xsrc, out);
     EVREP_LAUNCH_CHECK();
     return EVREP_OK;
