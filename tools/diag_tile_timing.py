@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""Where the register-resident TAF tile kernel (taf_tile_pk_kernel) spends its cycles, per role (diagnostic build only):
+"""Where a register-resident TAF tile kernel spends its cycles, per role (diagnostic build only):
    EVREP_NVCC_EXTRA=-DEVREP_TILE_TIMING python -m frlw_evd_b200.build --force && python tools/diag_tile_timing.py
-Averages over the tile CTAs the cycle counters of accumulate thread 0 and consumer thread 0."""
+Averages over the tile CTAs the cycle counters of accumulate thread 0 and consumer thread 0.  The counters are compiled
+into the packed-accumulator variant (taf_tile_pk_kernel, selected here through EVREP_TAF_TILE_KERNEL=pk); the figures of the
+default kernel in profiles/r2_tile_timing.txt came from the same macros placed temporarily in taf_tile_ws_kernel."""
 import ctypes
 import os
 import sys
@@ -16,6 +18,7 @@ from frlw_evd_b200 import _lib, ops, synth  # noqa: E402
 
 
 def main():
+    os.environ["EVREP_TAF_TILE_KERNEL"] = "pk"
     seconds, rate = 10.0, 1e7
     t, x, y, p = bench.get_stream(1002, seconds, rate)
     windows = bench.plan(synth.pack_dat_records(t, x, y, p), seconds)
