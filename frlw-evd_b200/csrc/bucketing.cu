@@ -198,9 +198,19 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
         const uint32_t ym = ev.ymap ? ev.ymap[i] : (uint32_t)i;
         s_row[i] = ym < H ? ym * W : kOffGrid;
     }
-    const uint32_t col_addr = smem_u32(s_col), row_addr = smem_u32(s_row);
-    const uint32_t n_cols = (uint32_t)lut_w, n_rows = (uint32_t)lut_h;
-    const uint32_t tile_mul = pl.tile_mul, P = (uint32_t)pl.P, n_tiles = (uint32_t)pl.n_tiles;
+    uint32_t col_addr = smem_u32(s_col), row_addr = smem_u32(s_row);
+    uint32_t n_cols = (uint32_t)lut_w, n_rows = (uint32_t)lut_h;
+    uint32_t tile_mul = pl.tile_mul, P = (uint32_t)pl.P, n_tiles = (uint32_t)pl.n_tiles;
+    // Per-event constants pinned in registers: left to itself the compiler re-derives them for every event (the shared
+    // window base through S2UR / ULEA, the kernel parameters through LDCU): a fifth of the pass's instructions.
+    uint32_t k_mul = pl.div_abin.mul, k_sh1 = pl.div_abin.sh1, k_sh2 = pl.div_abin.sh2, k_abin = pl.abin, k_hw = W * H;
+    asm volatile("" : "+r"(col_addr), "+r"(row_addr), "+r"(n_cols), "+r"(n_rows));
+    asm volatile("" : "+r"(tile_mul), "+r"(P), "+r"(n_tiles), "+r"(k_hw));
+    asm volatile("" : "+r"(k_mul), "+r"(k_sh1), "+r"(k_sh2), "+r"(k_abin));
+    auto div_abin = [&](uint32_t n) -> uint32_t {      // FastDiv::div with the constants above
+        const uint32_t t1 = __umulhi(k_mul, n);
+        return (t1 + ((n - t1) >> k_sh1)) >> k_sh2;
+    };
 
     for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const int64_t c0 = ev_first + (int64_t)chunk * (kBucketThreads * kBucketPerThread);
@@ -310,7 +320,7 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
             pol = (pw[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
             if (xv >= n_cols || yv >= n_rows || pol > 1u) return false;
             pix = lds_u32(col_addr + xv * 4u) + lds_u32(row_addr + yv * 4u);
-            return pix < HW;
+            return pix < k_hw;
         };
         // tile of a pixel: one multiply when the host proved the magic number exact for this grid
         auto tile_of = [&](uint32_t pix) -> uint32_t { return tile_mul ? __umulhi(pix, tile_mul) : pl.div_P.div(pix); };
@@ -325,9 +335,9 @@ taf_bucket_kernel(SoA ev, StreamPlan pl, int64_t ev_first, int64_t ev_last, int 
                 uint32_t pix, pol;
                 if (locate(k, pix, pol)) {
                     const uint32_t u = max(tt[k], start32) - start32;
-                    const uint32_t z = min(pl.div_abin.div(u), zmax);
+                    const uint32_t z = min(div_abin(u), zmax);
                     const uint32_t tile = tile_of(pix);
-                    if (kScatter || kSave) rec[k] = (min(u - z * pl.abin, kDMax) << 14) | ((pix - tile * P) << 1) | pol;
+                    if (kScatter || kSave) rec[k] = (min(u - z * k_abin, kDMax) << 14) | ((pix - tile * P) << 1) | pol;
                     deposit(k, tile, wi.binbase + (int)z);
                 }
                 if (kSave && vec_ok && (k & 3) == 3) {
