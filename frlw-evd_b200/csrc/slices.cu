@@ -132,9 +132,13 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
         const uint32_t ym = ev.ymap ? ev.ymap[i] : (uint32_t)i;
         s_row[i] = ym < H ? ym * W : kOffGrid;
     }
-    const uint32_t col_addr = smem_u32(s_col), row_addr = smem_u32(s_row);
-    const uint32_t n_cols = (uint32_t)lut_w, n_rows = (uint32_t)lut_h;
-    const uint32_t tile_mul = sp.tile_mul, P = (uint32_t)sp.P;
+    uint32_t col_addr = smem_u32(s_col), row_addr = smem_u32(s_row), hist_addr = smem_u32(hist);
+    uint32_t n_cols = (uint32_t)lut_w, n_rows = (uint32_t)lut_h;
+    uint32_t tile_mul = sp.tile_mul, P = (uint32_t)sp.P, k_hw = HW;
+    // per-event constants pinned in registers (see taf_bucket_kernel): the compiler otherwise re-derives the shared
+    // window base and re-loads the kernel parameters for every event
+    asm volatile("" : "+r"(col_addr), "+r"(row_addr), "+r"(hist_addr), "+r"(n_cols), "+r"(n_rows));
+    asm volatile("" : "+r"(tile_mul), "+r"(P), "+r"(k_hw));
     const int n_tiles = sp.n_tiles;
     const uint32_t n_slices = sp.status[1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -226,7 +230,7 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
             const uint32_t pol = (pw[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
             if (i < lo || i >= hi || xv >= n_cols || yv >= n_rows || pol > 1u) continue;
             const uint32_t pix = lds_u32(col_addr + xv * 4u) + lds_u32(row_addr + yv * 4u);
-            if (pix >= HW) continue;
+            if (pix >= k_hw) continue;
             // d = t - bin start; an event whose time lies outside its bin's edges is either clamped (first / last
             // bin of a window) or evidence that the input is not ordered in time
             uint32_t d;
@@ -246,7 +250,7 @@ slice_sort_kernel(SoA ev, SlicePlan sp, int64_t n_events, int lut_w, int lut_h, 
             big |= d > kPackedDMax ? 1u : 0u;
             const uint32_t tile = tile_mul ? __umulhi(pix, tile_mul) : sp.div_P.div(pix);
             rec[k] = kBinMajor ? (d << 14) | ((pix - tile * P) << 1) | pol : (d << 14) | (pol * P + (pix - tile * P));
-            slot[k] = (tile << 14) | atomicAdd(&hist[tile], 1u);
+            slot[k] = (tile << 14) | satom_add(hist_addr + tile * 4u, 1u);
         }
         if (strays) atomicAdd(sp.status, strays);
         if (big) s_flags = 1u;
