@@ -148,7 +148,7 @@ ev_slice_tile_kernel(const __grid_constant__ EvSliceParams tp) {
                 const uint32_t pol = cell_px >= Pu ? 1u : 0u, lp = cell_px - pol * Pu;
                 const int32_t rel = off + (int32_t)(rec >> 14);
                 // (t - t0) / tw in float64 (:141) then .float() (:23): reciprocal + one Newton step
-                const double dd = (double)(rel < 0 ? 0 : rel);
+                const double dd = __int2double_rn(rel < 0 ? 0 : rel);
                 const double q0 = dd * inv_tw;
                 const float tn = (float)fma(fma(-q0, tw, dd), inv_tw, q0);
                 const float ts = Kf * tn;                                        // t* = K * t
@@ -189,7 +189,7 @@ ev_slice_tile_kernel(const __grid_constant__ EvSliceParams tp) {
                     if (c4 >= p4) { c4 -= p4; ++row; }
                     const uint4 lo = reinterpret_cast<uint4*>(acc)[i];
                     const uint32_t wr = acc_hi[i];
-                    if (lo.x | lo.y | lo.z | lo.w) reinterpret_cast<uint4*>(acc)[i] = make_uint4(0u, 0u, 0u, 0u);
+                    reinterpret_cast<uint4*>(acc)[i] = make_uint4(0u, 0u, 0u, 0u);
                     if (wr) acc_hi[i] = 0u;
                     if (c4 * 4u < npix) {
                         float4 v;
