@@ -196,11 +196,15 @@ ev_slice_tile_kernel(const __grid_constant__ EvSliceParams tp) {
                         if (wr == 0u) {
                             // no wrap in these four cells (the usual case).  Scaling by 2^-27 commutes with every rounding
                             // of div5_mul255, so it is folded into the last factor: same bits, one multiply less
-                            auto fast = [](uint32_t lo_word) -> float {
-                                const float a = (float)lo_word, q = a * 0.2f;
-                                return fmaf(fmaf(-q, 5.0f, a), 0.2f, q) * (255.0f / kEvsUnit);
+                            // (packed f32x2 arithmetic: the kernel is bound by instruction issue, each lane rounds like FMUL / FFMA)
+                            auto fast2 = [](uint32_t w0, uint32_t w1) -> float2 {
+                                const float2 a = make_float2((float)w0, (float)w1), fifth = make_float2(0.2f, 0.2f);
+                                const float2 q = __fmul2_rn(a, fifth);
+                                const float2 r = __ffma2_rn(q, make_float2(-5.0f, -5.0f), a);
+                                return __fmul2_rn(__ffma2_rn(r, fifth, q), make_float2(255.0f / kEvsUnit, 255.0f / kEvsUnit));
                             };
-                            v.x = fast(lo.x); v.y = fast(lo.y); v.z = fast(lo.z); v.w = fast(lo.w);
+                            const float2 v01 = fast2(lo.x, lo.y), v23 = fast2(lo.z, lo.w);
+                            v.x = v01.x; v.y = v01.y; v.z = v23.x; v.w = v23.y;
                         } else {
                             v.x = value(lo.x, wr & 0xFFu); v.y = value(lo.y, (wr >> 8) & 0xFFu);
                             v.z = value(lo.z, (wr >> 16) & 0xFFu); v.w = value(lo.w, wr >> 24);
